@@ -1,0 +1,355 @@
+#!/usr/bin/env python3
+"""
+bench.py -- Mpixels/s of the rational-Bloom insert+query hot path on 4K YUV444 inter-frames.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path (K1 threshold+count -> exact (k,l,T) -> K2 insert -> K3 query
+-> K3b witness [-> NCCL all-gather of the bit arrays when N > 1]) over one synthetic stream of
+`--frames` 4K YUV444 frames (BASELINE.json configs[2]: 300 frames, p = 0.05, threshold 3.0), i.e.
+frames-1 inter-frame pairs.  `value` is measured with the stream resident in HBM; `e2e` repeats it
+through the host-buffer API call with the H2D / D2H copies inside the timed region.
+
+N > 1 is launched by torchrun (one process per GPU); every rank encodes its own stream (weak
+scaling), time = max over ranks of the CUDA-event time, value = all ranks' pixels / that time.
+
+--impl reference times the reference's CPU implementation (oracle/ref_port.py: the loop-for-loop
+Python port with python-xxhash; the reference itself is Python source that does not travel) on the
+box's host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mpixels/s bloom insert+query, 4K YUV444 inter-frame"
+BYTES_PER_PIXEL = 6            # both frames of the pair read once, 2 * 3 * sizeof(uint8)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------ synthetic stream
+def fill_stream(frames: np.ndarray, seed: int, one_in: int = 20) -> None:
+    """frames[t] = frames[t-1] with Bernoulli(1/one_in) pixels having Y,U,V += 64 (mod 256)."""
+    nfr, h, w, _ = frames.shape
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = ((yy * 3 + xx * 2) % 240).astype(np.uint8)
+    frames[0, :, :, 0] = base
+    frames[0, :, :, 1] = base // 2 + 7
+    frames[0, :, :, 2] = base // 3 + 90
+    frames[0] += rng.integers(0, 8, (h, w, 3), dtype=np.uint8)
+    for t in range(1, nfr):
+        r = np.random.default_rng(seed + t)
+        d = (r.integers(0, one_in, (h, w), dtype=np.uint8) == 0).view(np.uint8) * np.uint8(64)
+        np.add(frames[t - 1], d[:, :, None], out=frames[t])      # uint8 arithmetic wraps
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.tmp.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        if sm:
+            hot = sorted(sm)[len(sm) // 2:]             # samples under load: upper half
+            out.update(sm_mhz=float(np.median(hot)), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------ CPU baseline (reference port on host cores)
+def _cpu_worker(args):
+    seed, rows, width = args
+    from oracle import ref_port
+    rng = np.random.default_rng(seed)
+    prev = rng.integers(0, 256, (rows, width, 3), dtype=np.uint8)
+    curr = prev.copy()
+    ch = rng.integers(0, 20, (rows, width), dtype=np.uint8) == 0
+    curr[ch] += 64
+    t0 = time.perf_counter()
+    px = ref_port.encode_pair(prev, curr, 3.0)
+    return px, time.perf_counter() - t0
+
+
+def cpu_reference_sample(cores: int, bands_per_core: int, rows: int, width: int, seed: int = 1000):
+    """Each task = one `rows` x `width` band of a 4K YUV444 frame pair (p = 0.05) through the reference port."""
+    import multiprocessing as mp
+    tasks = [(seed + i, rows, width) for i in range(cores * bands_per_core)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_worker, tasks, chunksize=1)
+    wall = time.perf_counter() - t0
+    px = sum(r[0] for r in res)
+    return px / wall / 1e6, px, wall
+
+
+def cpu_c_oracle_sample(cores: int, frames: np.ndarray):
+    """Extra, stronger CPU number: the C oracle (oracle/rbf_oracle.c), one frame pair per thread."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import c_oracle as co
+
+    def one(t):
+        m, _ = co.frame_diff_mask(frames[t], frames[t + 1], 3.0)
+        co.compress(m.reshape(-1))
+        return m.size
+    n = min(cores, frames.shape[0] - 1)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(n) as ex:
+        px = sum(ex.map(one, range(n)))
+    return px / (time.perf_counter() - t0) / 1e6, n
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU path (ported loop for loop) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    use = min(cores, 64)
+    rows = 68                                   # 68 x 3840 = 261 120 px per task: ~0.4 s of reference Python
+    vals = []
+    for i in range(args.warmup + args.steps):
+        mps, px, wall = cpu_reference_sample(use, 1, rows, args.width, seed=5000 + 100 * i)
+        if i >= args.warmup:
+            vals.append((mps, px, wall))
+    value = float(np.mean([v[0] for v in vals]))
+    ms = float(np.mean([v[2] for v in vals]) * 1e3)
+    from oracle import ref_port
+    sample = "%d bands of %dx%d px (one per core, p=0.05, threshold 3.0) per step" % (use, rows, args.width)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "4K (3840x2160) YUV444 inter-frame stream, p=0.05, threshold=3.0; bounded sample: " + sample},
+            "cpu_baseline": {"value": value, "unit": "Mpixels/s", "cores": use, "kind": "port",
+                             "sample": sample + "; " + ref_port.HASH_IMPL},
+            "e2e": {"value": value, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ ours
+def pinned_array(cabi, shape, dtype=np.uint8):
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    cabi.check(cabi.lib().rbf_malloc_host(cabi.ctx(), nbytes, C.byref(p)), cabi.ctx())
+    buf = (C.c_uint8 * nbytes).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape), p
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist                 # rendezvous / barriers only; the data path is the library's NCCL
+        dist.init_process_group(backend="gloo")
+    import new_bloom_filter_repo_b200 as pkg
+    from new_bloom_filter_repo_b200 import _cabi as cabi, distributed as rdist
+    L, ctx = cabi.lib(), cabi.ctx()
+    info = cabi.device_info()
+    H, W, F = args.height, args.width, args.frames
+    n = H * W
+    pairs = F - 1
+    cabi.check(L.rbf_set_option(ctx, b"k1_variant", args.k1_variant), ctx)
+
+    frames, pin = pinned_array(cabi, (F, H, W, 3))
+    fill_stream(frames, seed=3 + 1000 * rank)
+    st = pkg.FrameStream(H, W, 3, np.uint8, max_frames=F)
+    st.upload(frames)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        cabi.check(L.rbf_sync(ctx), ctx)
+
+    # multi-GPU: one all-gather of the packed bit arrays per step
+    send = recv = None
+    slot = 0
+    res = st.encode_consecutive(F, 3.0)
+    if world > 1:
+        import torch
+        rdist.init_nccl_from_torch(dist)
+        t = torch.tensor([max((r.l + 7) // 8 for r in res)], dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        slot = (int(t.item()) + 15) // 16 * 16
+        send = rdist.DeviceBuffer(slot * pairs)
+        recv = rdist.DeviceBuffer(slot * pairs * world)
+
+    def step():
+        r = st.encode_consecutive(F, 3.0)
+        if world > 1:
+            cabi.check(L.rbf_stream_allgather_bitmaps(st._h, pairs, slot, send.ptr, recv.ptr), ctx)
+        return r
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    cabi.check(L.rbf_reset_counters(ctx), ctx)
+    stage_acc = {}
+    cabi.check(L.rbf_timer_start(ctx), ctx)
+    for _ in range(args.steps):
+        res = step()
+        for k_, v in st.stage_ms().items():
+            stage_acc[k_] = stage_acc.get(k_, 0.0) + v
+    ms = C.c_double()
+    cabi.check(L.rbf_timer_stop_ms(ctx, C.byref(ms)), ctx)
+    launches = int(L.rbf_get_counter(ctx, b"kernel_launches"))
+    barrier()
+    clocks = sampler.stop()
+    ms_local = ms.value
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms_local], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    else:
+        ms_total = ms_local
+    ms_per_step = ms_total / args.steps
+    total_px = pairs * n * world
+    value = total_px / (ms_per_step * 1e-3) / 1e6
+    stage = {k_: v / args.steps for k_, v in stage_acc.items()}
+
+    # ---- end to end: host frames -> C-ABI call -> packed outputs on the host, copies inside the timed region
+    bm_slot = (max((r.l + 7) // 8 for r in res) + 15) // 16 * 16
+    wt_slot = (max((r.wlen + 7) // 8 for r in res) + 15) // 16 * 16
+    out_bm, pin_bm = pinned_array(cabi, (pairs, bm_slot))
+    out_wt, pin_wt = pinned_array(cabi, (pairs, wt_slot))
+    e2e_steps = max(1, min(args.steps, 3))
+    st.encode_host(frames, 3.0, bitmap_slot=bm_slot, witness_slot=wt_slot, out_bitmaps=out_bm, out_witness=out_wt)
+    barrier()
+    cabi.check(L.rbf_reset_counters(ctx), ctx)
+    cabi.check(L.rbf_timer_start(ctx), ctx)
+    for _ in range(e2e_steps):
+        st.encode_host(frames, 3.0, bitmap_slot=bm_slot, witness_slot=wt_slot, out_bitmaps=out_bm, out_witness=out_wt)
+    ms2 = C.c_double()
+    cabi.check(L.rbf_timer_stop_ms(ctx, C.byref(ms2)), ctx)
+    h2d = int(L.rbf_get_counter(ctx, b"h2d_bytes")) // e2e_steps
+    d2h = int(L.rbf_get_counter(ctx, b"d2h_bytes")) // e2e_steps
+    e2e_ms = ms2.value / e2e_steps
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = total_px / (e2e_ms * 1e-3) / 1e6
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        q_ms = stage["k3_query"]
+        coded_px = sum(r.n for r in res if not r.raw)
+        achieved = coded_px * BYTES_PER_PIXEL / (q_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": "4K (3840x2160) YUV444 %d-frame synthetic stream -> %d inter-frame pairs per GPU, p=0.05, "
+                                   "threshold=3.0, seeds 0x12345678/0x87654321/999 (BASELINE configs[2]%s)" %
+                                   (F, pairs, "; frames sharded per rank + one NCCL all-gather of the bit arrays" if world > 1 else ""),
+                       "height": H, "width": W, "frames": F, "pairs_per_gpu": pairs, "parallelism": "frame-sharded x%d" % world,
+                       "l2_policy": "inputs larger than L2: %.2f GB of frames per step, no flush needed" % (F * n * 3 / 1e9),
+                       "k1_variant": "tma-bulk-ring" if args.k1_variant == 1 else "ldg128",
+                       "mean_l_bits": float(np.mean([r.l for r in res])), "mean_witness_bits": float(np.mean([r.wlen for r in res]))},
+            "roofline": {"bound": "hbm", "kernel": "k_query", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": coded_px * BYTES_PER_PIXEL, "launch_ms": q_ms,
+                         "pipeline_frac": value * 1e6 * BYTES_PER_PIXEL / 1e9 / world / peak,
+                         "stage_ms": stage},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "rbf_stream_encode_host (pinned host frames in, packed "
+                    "bitmaps + witnesses out)"},
+            "gpu_launches": launches,
+            "device": info["name"],
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            use = min(cores, 64)
+            mps, px, wall = cpu_reference_sample(use, 8, 68, W)
+            line["cpu_baseline"] = {"value": mps, "unit": "Mpixels/s", "cores": use, "kind": "port",
+                                    "sample": "%d bands of 68x%d px (8 per core, p=0.05) through oracle/ref_port.py in %.1f s"
+                                              % (8 * use, W, wall)}
+            try:
+                cm, cn = cpu_c_oracle_sample(use, frames[: min(F, use + 1)])
+                line["cpu_baseline_c_oracle"] = {"value": cm, "unit": "Mpixels/s", "cores": cn, "kind": "port",
+                                                 "sample": "%d full 4K pairs, one per thread, oracle/rbf_oracle.c" % cn}
+            except Exception as e:       # pragma: no cover
+                line["cpu_baseline_c_oracle"] = {"error": str(e)}
+        print(json.dumps(line))
+    st.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=300)
+    ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--width", type=int, default=3840)
+    ap.add_argument("--k1-variant", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,875 @@
+// rbf_api.cu -- the C ABI (include/rbf_b200.h) and the host side of the pipeline.
+// Host code mirrors the reference's float expressions exactly (compile with -ffp-contract=off).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rbf_b200.h"
+#include "rbf_kernels.cuh"
+
+using namespace rbf;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+struct rbf_ctx {
+    int device = -1;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaDeviceProp prop;
+    int sm_count = 0;
+    int k1_variant = 0;
+    int k1_only = 0;        // stop after K1 (mask + counts): VideoFrameCompressor._calculate_frame_diff
+    int mask_mode = 0;      // 0: |dY| > thr (ivc:808); 1: additionally any byte of the pixel differs
+    int query_smem_cap = 0;
+    char err[512];
+    int64_t launches = 0, h2d = 0, d2h = 0;
+    std::vector<void*> scratch;
+    std::vector<size_t> scratch_sz;
+    void* pinned = nullptr;
+    size_t pinned_sz = 0;
+    // NCCL (dlopen'ed)
+    void* nccl_lib = nullptr;
+    void* nccl_comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+static int set_err(rbf_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    snprintf(g_err, sizeof g_err, "%s", buf);
+    if (c) snprintf(c->err, sizeof c->err, "%s", buf);
+    return code;
+}
+#define CK(ctx, call)                                                                                           \
+    do {                                                                                                        \
+        cudaError_t e__ = (call);                                                                               \
+        if (e__ != cudaSuccess)                                                                                 \
+            return set_err(ctx, e__ == cudaErrorMemoryAllocation ? RBF_ERR_OOM : RBF_ERR_CUDA, "%s:%d %s: %s", \
+                           __FILE__, __LINE__, #call, cudaGetErrorString(e__));                               \
+    } while (0)
+#define LAUNCH(ctx, call)  \
+    do {                   \
+        CK(ctx, call);     \
+        (ctx)->launches++; \
+    } while (0)
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int scratch_get(rbf_ctx* c, int slot, size_t bytes, void** out) {
+    if ((int)c->scratch.size() <= slot) { c->scratch.resize(slot + 1, nullptr); c->scratch_sz.resize(slot + 1, 0); }
+    if (c->scratch_sz[slot] < bytes) {
+        if (c->scratch[slot]) CK(c, cudaFree(c->scratch[slot]));
+        c->scratch[slot] = nullptr; c->scratch_sz[slot] = 0;
+        size_t nb = align_up(bytes + (bytes >> 2), 256);
+        CK(c, cudaMalloc(&c->scratch[slot], nb));
+        c->scratch_sz[slot] = nb;
+    }
+    *out = c->scratch[slot];
+    return RBF_OK;
+}
+static int pinned_get(rbf_ctx* c, size_t bytes, void** out) {
+    if (c->pinned_sz < bytes) {
+        if (c->pinned) CK(c, cudaFreeHost(c->pinned));
+        c->pinned = nullptr; c->pinned_sz = 0;
+        size_t nb = align_up(bytes * 2, 4096);
+        CK(c, cudaMallocHost(&c->pinned, nb));
+        c->pinned_sz = nb;
+    }
+    *out = c->pinned;
+    return RBF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// exact host-side scalars
+// ------------------------------------------------------------------------------------------
+// correctly rounded double of h / (2^64 - 1): Python int/int true division (ivc:95).  The exact
+// quotient is h*2^-64*(1 + 2^-64 + ...), a hair above h*2^-64, so round h to 53 bits, ties up.
+static double unit_div(uint64_t h) {
+    if (h == 0) return 0.0;
+    const int bl = 64 - __builtin_clzll(h);
+    if (bl <= 53) return ldexp((double)h, -64);
+    const int sh = bl - 53;
+    uint64_t top = h >> sh;
+    const uint64_t rem = h & ((1ULL << sh) - 1), half = 1ULL << (sh - 1);
+    if (rem >= half) top += 1;
+    return ldexp((double)top, sh - 64);
+}
+
+extern "C" uint64_t rbf_activation_threshold(double p_act) {
+    if (!(p_act > 0.0)) return 0;                       // also NaN
+    if (unit_div(UINT64_MAX) < p_act) return UINT64_MAX;
+    uint64_t lo = 0, hi = UINT64_MAX;                   // smallest h with unit_div(h) >= p_act
+    while (lo < hi) {
+        const uint64_t mid = lo + (hi - lo) / 2;
+        if (unit_div(mid) < p_act) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+static const double kPStar = 0.32453;                  // ivc:150
+
+// _calculate_optimal_params (ivc:161-196); returns l (0 => the (0, 0) result)
+static uint64_t optimal_kl(uint64_t n, double p, double* k_out) {
+    *k_out = 0.0;
+    if (p <= 0.0001) return 0;
+    if (p >= kPStar) return 0;
+    const double q = 1 - p;
+    const double L = log(2.0);
+    const double k = log2(q * pow(L, 2.0) / p);         // ivc:185
+    if (isnan(k) || k <= 0) return 0;
+    const double gamma = 1 / L;
+    const double lf = p * (double)n * k * gamma;        // ivc:193, evaluated left to right
+    const uint64_t l = (uint64_t)lf;
+    *k_out = k > 0.1 ? k : 0.1;
+    return l > 1 ? l : 1;
+}
+
+extern "C" int rbf_optimal_params(uint64_t n, uint64_t ones, double* p_out, double* k_out, uint64_t* l_out) {
+    const double p = (double)ones / (double)n;          // ivc:212
+    double k = 0.0;
+    uint64_t l = 0;
+    int coded = 0;
+    if (!(p >= kPStar)) {                               // ivc:215
+        l = optimal_kl(n, p, &k);
+        if (!(l == 0 || l >= n)) coded = 1;             // ivc:223
+    }
+    if (!coded) { k = 0.0; l = 0; }
+    if (p_out) *p_out = p;
+    if (k_out) *k_out = k;
+    if (l_out) *l_out = l;
+    return coded;
+}
+
+extern "C" uint64_t rbf_xxh64(const void* data, uint64_t len, uint64_t seed) {
+    return xxh64_bytes((const uint8_t*)data, (uint32_t)len, seed);
+}
+extern "C" uint64_t rbf_hash_decimal(uint32_t item, uint64_t seed) { return xxh64_decimal(item, seed); }
+extern "C" uint64_t rbf_hash_decimal_century(uint32_t item, uint64_t seed) {
+    const Century c = make_century(item / 100u);
+    return finish(c.kind, decade_state(c, century_state(c, seed), seed, (item / 10u) % 10u), seed, item % 10u);
+}
+extern "C" uint32_t rbf_probe_index(uint64_t h1, uint64_t h2, uint32_t i, uint32_t size) {
+    if (size == 0) return 0;
+    return probe_index(h1, h2, i, make_fastmod(size));
+}
+extern "C" int rbf_abi_version(void) { return RBF_ABI_VERSION; }
+extern "C" const char* rbf_last_global_error(void) { return g_err; }
+
+// fill the filter part of a job from (size, k*)  (ivc:47-63)
+static void job_set_filter(FrameJob& J, uint64_t size, double k_star, const rbf_seeds& sd) {
+    J.l = (uint32_t)size;
+    const double fl = floor(k_star);
+    J.floor_k = (uint32_t)(fl < 0 ? 0 : fl);
+    const double p_act = k_star - fl;                   // ivc:58
+    J.has_act = p_act > 0.0 ? 1u : 0u;
+    J.act_T = rbf_activation_threshold(p_act);
+    J.seed1 = sd.h1; J.seed2 = sd.h2; J.seedA = sd.act;
+    J.fm = make_fastmod((uint32_t)size);
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+extern "C" int rbf_ctx_create(int device, rbf_ctx** out) {
+    if (!out) return set_err(nullptr, RBF_ERR_INVALID, "rbf_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(nullptr, RBF_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return set_err(nullptr, RBF_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+    rbf_ctx* c = new rbf_ctx();
+    c->err[0] = 0;
+    c->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&c->prop, device)) != cudaSuccess) {
+        delete c;
+        return set_err(nullptr, RBF_ERR_CUDA, "cudaSetDevice/GetDeviceProperties: %s", cudaGetErrorString(e));
+    }
+    if (c->prop.major < 10) {
+        int maj = c->prop.major, mn = c->prop.minor;
+        delete c;
+        return set_err(nullptr, RBF_ERR_NO_DEVICE, "device is sm_%d%d; this library is built for sm_100a only", maj, mn);
+    }
+    c->sm_count = c->prop.multiProcessorCount;
+    c->query_smem_cap = query_max_smem_bytes();
+    if ((e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
+        delete c;
+        return set_err(nullptr, RBF_ERR_CUDA, "stream/event create: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return RBF_OK;
+}
+
+extern "C" void rbf_ctx_destroy(rbf_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    rbf_nccl_destroy(c);
+    for (void* p : c->scratch) if (p) cudaFree(p);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+}
+extern "C" const char* rbf_last_error(const rbf_ctx* c) { return c ? c->err : g_err; }
+
+extern "C" int rbf_device_info(rbf_ctx* c, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor,
+                               uint64_t* total_mem) {
+    if (!c) return set_err(nullptr, RBF_ERR_INVALID, "ctx is NULL");
+    if (name && name_len > 0) snprintf(name, name_len, "%s", c->prop.name);
+    if (sm_count) *sm_count = c->sm_count;
+    if (cc_major) *cc_major = c->prop.major;
+    if (cc_minor) *cc_minor = c->prop.minor;
+    if (total_mem) *total_mem = c->prop.totalGlobalMem;
+    return RBF_OK;
+}
+extern "C" int rbf_set_option(rbf_ctx* c, const char* key, int64_t v) {
+    if (!c || !key) return set_err(c, RBF_ERR_INVALID, "rbf_set_option: NULL");
+    if (!strcmp(key, "k1_variant")) { c->k1_variant = (int)v; return RBF_OK; }
+    if (!strcmp(key, "k1_only")) { c->k1_only = v ? 1 : 0; return RBF_OK; }
+    if (!strcmp(key, "mask_mode")) { c->mask_mode = v ? 1 : 0; return RBF_OK; }
+    if (!strcmp(key, "query_smem_bytes")) {
+        c->query_smem_cap = (int)((v <= 0 || v > query_max_smem_bytes()) ? query_max_smem_bytes() : v);
+        return RBF_OK;
+    }
+    return set_err(c, RBF_ERR_INVALID, "unknown option %s", key);
+}
+extern "C" int64_t rbf_get_counter(rbf_ctx* c, const char* key) {
+    if (!c || !key) return -1;
+    if (!strcmp(key, "kernel_launches")) return c->launches;
+    if (!strcmp(key, "h2d_bytes")) return c->h2d;
+    if (!strcmp(key, "d2h_bytes")) return c->d2h;
+    return -1;
+}
+extern "C" int rbf_reset_counters(rbf_ctx* c) { if (!c) return RBF_ERR_INVALID; c->launches = c->h2d = c->d2h = 0; return RBF_OK; }
+extern "C" int rbf_sync(rbf_ctx* c) { if (!c) return RBF_ERR_INVALID; CK(c, cudaStreamSynchronize(c->st)); return RBF_OK; }
+extern "C" int rbf_timer_start(rbf_ctx* c) { if (!c) return RBF_ERR_INVALID; CK(c, cudaEventRecord(c->ev0, c->st)); return RBF_OK; }
+extern "C" int rbf_timer_stop_ms(rbf_ctx* c, double* ms) {
+    if (!c || !ms) return RBF_ERR_INVALID;
+    CK(c, cudaEventRecord(c->ev1, c->st));
+    CK(c, cudaEventSynchronize(c->ev1));
+    float f = 0;
+    CK(c, cudaEventElapsedTime(&f, c->ev0, c->ev1));
+    *ms = f;
+    return RBF_OK;
+}
+
+// memory
+extern "C" int rbf_malloc(rbf_ctx* c, size_t bytes, void** d) { if (!c || !d) return RBF_ERR_INVALID; CK(c, cudaSetDevice(c->device)); CK(c, cudaMalloc(d, bytes ? bytes : 1)); return RBF_OK; }
+extern "C" int rbf_free(rbf_ctx* c, void* d) { if (!c) return RBF_ERR_INVALID; if (d) CK(c, cudaFree(d)); return RBF_OK; }
+extern "C" int rbf_malloc_host(rbf_ctx* c, size_t bytes, void** h) { if (!c || !h) return RBF_ERR_INVALID; CK(c, cudaMallocHost(h, bytes ? bytes : 1)); return RBF_OK; }
+extern "C" int rbf_free_host(rbf_ctx* c, void* h) { if (!c) return RBF_ERR_INVALID; if (h) CK(c, cudaFreeHost(h)); return RBF_OK; }
+extern "C" int rbf_memcpy_h2d(rbf_ctx* c, void* d, const void* h, size_t n) {
+    if (!c) return RBF_ERR_INVALID;
+    CK(c, cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, c->st)); CK(c, cudaStreamSynchronize(c->st)); c->h2d += n; return RBF_OK;
+}
+extern "C" int rbf_memcpy_d2h(rbf_ctx* c, void* h, const void* d, size_t n) {
+    if (!c) return RBF_ERR_INVALID;
+    CK(c, cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c->st)); CK(c, cudaStreamSynchronize(c->st)); c->d2h += n; return RBF_OK;
+}
+extern "C" int rbf_memset(rbf_ctx* c, void* d, int v, size_t n) { if (!c) return RBF_ERR_INVALID; CK(c, cudaMemsetAsync(d, v, n, c->st)); return RBF_OK; }
+
+// ------------------------------------------------------------------------------------------
+// one filter
+// ------------------------------------------------------------------------------------------
+struct rbf_filter {
+    rbf_ctx* c;
+    uint64_t size;
+    FrameJob job;          // host copy
+    FrameJob* d_job;
+    uint32_t* d_bits;      // LSB-first
+    size_t words;
+};
+
+extern "C" int rbf_filter_create(rbf_ctx* c, uint64_t size, double k_star, const rbf_seeds* sd, rbf_filter** out) {
+    if (!c || !sd || !out) return set_err(c, RBF_ERR_INVALID, "rbf_filter_create: NULL argument");
+    if (size == 0 || size > 0xffffffffULL) return set_err(c, RBF_ERR_INVALID, "filter size %llu outside [1, 2^32)", (unsigned long long)size);
+    if (!(k_star >= 0.0) || k_star > 1e6) return set_err(c, RBF_ERR_INVALID, "k_star %g not supported", k_star);
+    CK(c, cudaSetDevice(c->device));
+    rbf_filter* f = new rbf_filter();
+    f->c = c; f->size = size; f->words = align_up((size + 31) / 32 + 8, 32);
+    memset(&f->job, 0, sizeof f->job);
+    job_set_filter(f->job, size, k_star, *sd);
+    f->job.n = 0;
+    cudaError_t e = cudaMalloc(&f->d_bits, f->words * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_job, sizeof(FrameJob));
+    if (e != cudaSuccess) { delete f; return set_err(c, RBF_ERR_OOM, "rbf_filter_create: %s", cudaGetErrorString(e)); }
+    f->job.bits = f->d_bits;
+    CK(c, cudaMemsetAsync(f->d_bits, 0, f->words * 4, c->st));
+    CK(c, cudaMemcpyAsync(f->d_job, &f->job, sizeof(FrameJob), cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+    *out = f;
+    return RBF_OK;
+}
+extern "C" void rbf_filter_destroy(rbf_filter* f) {
+    if (!f) return;
+    cudaFree(f->d_bits); cudaFree(f->d_job);
+    delete f;
+}
+static int filter_items_u32(rbf_filter* f, const uint32_t* items, uint32_t count, uint8_t* out, int insert) {
+    rbf_ctx* c = f->c;
+    if (count == 0) return RBF_OK;
+    void *d_items, *d_res;
+    int rc;
+    if ((rc = scratch_get(c, 0, (size_t)count * 4, &d_items))) return rc;
+    if ((rc = scratch_get(c, 1, (size_t)count, &d_res))) return rc;
+    CK(c, cudaMemcpyAsync(d_items, items, (size_t)count * 4, cudaMemcpyHostToDevice, c->st)); c->h2d += (size_t)count * 4;
+    LAUNCH(c, launch_items_u32(f->d_job, (const uint32_t*)d_items, count, (uint8_t*)d_res, insert, c->st));
+    if (!insert) { CK(c, cudaMemcpyAsync(out, d_res, count, cudaMemcpyDeviceToHost, c->st)); c->d2h += count; }
+    CK(c, cudaStreamSynchronize(c->st));
+    return RBF_OK;
+}
+extern "C" int rbf_filter_add_indices(rbf_filter* f, const uint32_t* items, uint32_t count) {
+    if (!f || (!items && count)) return set_err(f ? f->c : nullptr, RBF_ERR_INVALID, "rbf_filter_add_indices: NULL");
+    return filter_items_u32(f, items, count, nullptr, 1);
+}
+extern "C" int rbf_filter_check_indices(rbf_filter* f, const uint32_t* items, uint32_t count, uint8_t* out) {
+    if (!f || ((!items || !out) && count)) return set_err(f ? f->c : nullptr, RBF_ERR_INVALID, "rbf_filter_check_indices: NULL");
+    return filter_items_u32(f, items, count, out, 0);
+}
+static int filter_items_str(rbf_filter* f, const uint8_t* blob, const uint64_t* offs, uint32_t count, int standard_k,
+                            uint8_t* out, int insert) {
+    rbf_ctx* c = f->c;
+    if (count == 0) return RBF_OK;
+    const size_t blob_bytes = (size_t)offs[count];
+    void *d_blob, *d_offs, *d_res;
+    int rc;
+    if ((rc = scratch_get(c, 0, blob_bytes + 16, &d_blob))) return rc;
+    if ((rc = scratch_get(c, 1, (size_t)count, &d_res))) return rc;
+    if ((rc = scratch_get(c, 2, ((size_t)count + 1) * 8, &d_offs))) return rc;
+    if (blob_bytes) { CK(c, cudaMemcpyAsync(d_blob, blob, blob_bytes, cudaMemcpyHostToDevice, c->st)); }
+    CK(c, cudaMemcpyAsync(d_offs, offs, ((size_t)count + 1) * 8, cudaMemcpyHostToDevice, c->st));
+    c->h2d += blob_bytes + ((size_t)count + 1) * 8;
+    LAUNCH(c, launch_items_str(f->d_job, (const uint8_t*)d_blob, (const uint64_t*)d_offs, count, (uint8_t*)d_res, insert,
+                               standard_k, c->st));
+    if (!insert) { CK(c, cudaMemcpyAsync(out, d_res, count, cudaMemcpyDeviceToHost, c->st)); c->d2h += count; }
+    CK(c, cudaStreamSynchronize(c->st));
+    return RBF_OK;
+}
+extern "C" int rbf_filter_add_strings(rbf_filter* f, const uint8_t* blob, const uint64_t* offs, uint32_t count, int standard_k) {
+    if (!f || (!offs && count)) return set_err(f ? f->c : nullptr, RBF_ERR_INVALID, "rbf_filter_add_strings: NULL");
+    return filter_items_str(f, blob, offs, count, standard_k, nullptr, 1);
+}
+extern "C" int rbf_filter_check_strings(rbf_filter* f, const uint8_t* blob, const uint64_t* offs, uint32_t count,
+                                        int standard_k, uint8_t* out) {
+    if (!f || ((!offs || !out) && count)) return set_err(f ? f->c : nullptr, RBF_ERR_INVALID, "rbf_filter_check_strings: NULL");
+    return filter_items_str(f, blob, offs, count, standard_k, out, 0);
+}
+extern "C" int rbf_filter_get_bits(rbf_filter* f, uint8_t* out) {
+    if (!f || !out) return set_err(f ? f->c : nullptr, RBF_ERR_INVALID, "rbf_filter_get_bits: NULL");
+    rbf_ctx* c = f->c;
+    void* d_bytes; int rc;
+    if ((rc = scratch_get(c, 0, f->size, &d_bytes))) return rc;
+    LAUNCH(c, launch_unpack_bits(f->d_bits, (uint8_t*)d_bytes, f->size, c->st));
+    CK(c, cudaMemcpyAsync(out, d_bytes, f->size, cudaMemcpyDeviceToHost, c->st)); c->d2h += f->size;
+    CK(c, cudaStreamSynchronize(c->st));
+    return RBF_OK;
+}
+extern "C" int rbf_filter_set_bits(rbf_filter* f, const uint8_t* in) {
+    if (!f || !in) return set_err(f ? f->c : nullptr, RBF_ERR_INVALID, "rbf_filter_set_bits: NULL");
+    rbf_ctx* c = f->c;
+    void* d_bytes; int rc;
+    if ((rc = scratch_get(c, 0, f->size, &d_bytes))) return rc;
+    CK(c, cudaMemcpyAsync(d_bytes, in, f->size, cudaMemcpyHostToDevice, c->st)); c->h2d += f->size;
+    CK(c, cudaMemsetAsync(f->d_bits, 0, f->words * 4, c->st));
+    LAUNCH(c, launch_pack_bytes((const uint8_t*)d_bytes, f->d_bits, f->size, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+    return RBF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// mask coder (host buffers)
+// ------------------------------------------------------------------------------------------
+
+static size_t bit_words_padded(uint64_t nbits) { return align_up((nbits + 31) / 32 + 8, 32); }   // >= 32 B of padding, 128 B multiple
+static size_t pass_words(uint64_t n) { return align_up(((n + 99) / 100) * 4, 32); }
+
+extern "C" int rbf_compress_mask(rbf_ctx* c, const uint8_t* mask, uint64_t n, const rbf_seeds* sd, double k_override,
+                                 uint64_t l_override, rbf_mask_info* info, uint8_t* bitmap_out, uint8_t* witness_out) {
+    if (!c || !mask || !sd || !info) return set_err(c, RBF_ERR_INVALID, "rbf_compress_mask: NULL argument");
+    if (n == 0 || n > 0xffffff00ULL) return set_err(c, RBF_ERR_INVALID, "n = %llu outside [1, 2^32-256]", (unsigned long long)n);
+    CK(c, cudaSetDevice(c->device));
+    memset(info, 0, sizeof *info);
+    info->n = n;
+    const size_t mw = bit_words_padded(n), pw = pass_words(n);
+    void *d_bytes, *d_mask, *d_bits, *d_pass, *d_wit, *d_small;
+    int rc;
+    if ((rc = scratch_get(c, 0, n, &d_bytes)) || (rc = scratch_get(c, 3, mw * 4, &d_mask)) ||
+        (rc = scratch_get(c, 4, mw * 4, &d_bits)) || (rc = scratch_get(c, 5, pw * 4, &d_pass)) ||
+        (rc = scratch_get(c, 6, mw * 4, &d_wit)) || (rc = scratch_get(c, 7, 4096, &d_small)))
+        return rc;
+    uint32_t* d_cnt = (uint32_t*)d_small;                         // [0] ones, [1] wlen
+    uint32_t* d_prefix = d_cnt + 4;                               // [2] cent_prefix
+    FrameJob* d_job = (FrameJob*)((uint8_t*)d_small + 256);
+    CK(c, cudaMemcpyAsync(d_bytes, mask, n, cudaMemcpyHostToDevice, c->st)); c->h2d += n;
+    CK(c, cudaMemsetAsync(d_mask, 0, mw * 4, c->st));
+    CK(c, cudaMemsetAsync(d_cnt, 0, 16, c->st));
+    LAUNCH(c, launch_pack_bytes((const uint8_t*)d_bytes, (uint32_t*)d_mask, n, c->st));
+    LAUNCH(c, launch_popcount((const uint32_t*)d_mask, (n + 31) / 32, d_cnt, c->st));
+    uint32_t h_cnt[4] = {0, 0, 0, 0};
+    CK(c, cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, c->st)); c->d2h += 16;
+    CK(c, cudaStreamSynchronize(c->st));
+    info->ones = h_cnt[0];
+    double p, k; uint64_t l;
+    int coded = rbf_optimal_params(n, info->ones, &p, &k, &l);
+    info->p = p;
+    if (k_override > 0.0 && !(p >= kPStar)) { k = k_override; l = l_override; coded = !(l == 0 || l >= n); }
+    if (!coded) { info->raw = 1; return RBF_OK; }
+    info->k = k; info->l = l;
+    FrameJob J; memset(&J, 0, sizeof J);
+    J.n = (uint32_t)n;
+    job_set_filter(J, l, k, *sd);
+    J.mask = (const uint32_t*)d_mask; J.bits = (uint32_t*)d_bits; J.pass = (uint32_t*)d_pass; J.witness = (uint32_t*)d_wit;
+    info->floor_k = J.floor_k; info->act_T = J.act_T;
+    const uint32_t ncent = (uint32_t)((n + 99) / 100);
+    uint32_t h_prefix[2] = {0, ncent};
+    CK(c, cudaMemcpyAsync(d_job, &J, sizeof J, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(d_prefix, h_prefix, 8, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemsetAsync(d_bits, 0, bit_words_padded(l) * 4, c->st));
+    CK(c, cudaMemsetAsync(d_wit, 0, mw * 4, c->st));
+    LAUNCH(c, launch_insert(d_job, 1, ncent, c->sm_count, c->st));
+    LAUNCH(c, launch_query(d_job, d_prefix, 1, ncent, c->sm_count, c->query_smem_cap, c->st));
+    LAUNCH(c, launch_witness(d_job, 1, d_cnt + 1, c->st));
+    CK(c, cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, c->st)); c->d2h += 16;
+    CK(c, cudaStreamSynchronize(c->st));
+    info->wlen = h_cnt[1];
+    // after K3b both streams are in packbits order; hand them back unpacked (ivc:266 returns bit_array, witness)
+    if (bitmap_out) {
+        LAUNCH(c, launch_unpack_bits_msb((const uint32_t*)d_bits, (uint8_t*)d_bytes, l, c->st));
+        CK(c, cudaMemcpyAsync(bitmap_out, d_bytes, l, cudaMemcpyDeviceToHost, c->st)); c->d2h += l;
+        CK(c, cudaStreamSynchronize(c->st));
+    }
+    if (witness_out && info->wlen) {
+        LAUNCH(c, launch_unpack_bits_msb((const uint32_t*)d_wit, (uint8_t*)d_bytes, info->wlen, c->st));
+        CK(c, cudaMemcpyAsync(witness_out, d_bytes, info->wlen, cudaMemcpyDeviceToHost, c->st)); c->d2h += info->wlen;
+        CK(c, cudaStreamSynchronize(c->st));
+    }
+    return RBF_OK;
+}
+
+extern "C" int rbf_decompress_mask(rbf_ctx* c, const uint8_t* bitmap, uint64_t l, const uint8_t* witness, uint64_t wlen,
+                                   uint64_t n, double k, const rbf_seeds* sd, uint8_t* out, uint64_t* consumed) {
+    if (!c || !bitmap || !sd || !out || (!witness && wlen)) return set_err(c, RBF_ERR_INVALID, "rbf_decompress_mask: NULL argument");
+    if (n == 0 || n > 0xffffff00ULL || l == 0 || l > 0xffffffffULL) return set_err(c, RBF_ERR_INVALID, "bad n/l");
+    if (!(k >= 0.0)) return set_err(c, RBF_ERR_INVALID, "bad k");
+    CK(c, cudaSetDevice(c->device));
+    const size_t mw = bit_words_padded(n), lw = bit_words_padded(l), ww = bit_words_padded(wlen), pw = pass_words(n);
+    const size_t big = n > l ? (n > wlen ? n : wlen) : (l > wlen ? l : wlen);
+    void *d_bytes, *d_out, *d_bits, *d_pass, *d_wit, *d_small;
+    int rc;
+    if ((rc = scratch_get(c, 0, big, &d_bytes)) || (rc = scratch_get(c, 3, mw * 4, &d_out)) ||
+        (rc = scratch_get(c, 4, lw * 4, &d_bits)) || (rc = scratch_get(c, 5, pw * 4, &d_pass)) ||
+        (rc = scratch_get(c, 6, ww * 4, &d_wit)) || (rc = scratch_get(c, 7, 4096, &d_small)))
+        return rc;
+    uint32_t* d_cnt = (uint32_t*)d_small;
+    uint32_t* d_prefix = d_cnt + 4;
+    FrameJob* d_job = (FrameJob*)((uint8_t*)d_small + 256);
+    CK(c, cudaMemsetAsync(d_bits, 0, lw * 4, c->st));
+    CK(c, cudaMemsetAsync(d_wit, 0, ww * 4, c->st));
+    CK(c, cudaMemsetAsync(d_out, 0, mw * 4, c->st));
+    CK(c, cudaMemcpyAsync(d_bytes, bitmap, l, cudaMemcpyHostToDevice, c->st)); c->h2d += l;
+    LAUNCH(c, launch_pack_bytes((const uint8_t*)d_bytes, (uint32_t*)d_bits, l, c->st));
+    if (wlen) {
+        CK(c, cudaMemcpyAsync(d_bytes, witness, wlen, cudaMemcpyHostToDevice, c->st)); c->h2d += wlen;
+        // witness values are used as bits: any non-zero byte other than 1 is not representable; the reference
+        // stores whatever the list holds (ivc:303); np.unpackbits output is 0/1 (ivc:1001-1002)
+        LAUNCH(c, launch_pack_bytes((const uint8_t*)d_bytes, (uint32_t*)d_wit, wlen, c->st));
+    }
+    FrameJob J; memset(&J, 0, sizeof J);
+    J.n = (uint32_t)n;
+    job_set_filter(J, l, k, *sd);
+    J.bits = (uint32_t*)d_bits; J.pass = (uint32_t*)d_pass; J.witness = (uint32_t*)d_wit; J.out_mask = (uint32_t*)d_out;
+    J.wlen_in = (uint32_t)wlen;
+    const uint32_t ncent = (uint32_t)((n + 99) / 100);
+    uint32_t h_prefix[2] = {0, ncent};
+    CK(c, cudaMemcpyAsync(d_job, &J, sizeof J, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(d_prefix, h_prefix, 8, cudaMemcpyHostToDevice, c->st));
+    LAUNCH(c, launch_query(d_job, d_prefix, 1, ncent, c->sm_count, c->query_smem_cap, c->st));
+    LAUNCH(c, launch_expand(d_job, 1, d_cnt, c->st));
+    LAUNCH(c, launch_unpack_bits((const uint32_t*)d_out, (uint8_t*)d_bytes, n, c->st));
+    uint32_t h_cnt = 0;
+    CK(c, cudaMemcpyAsync(out, d_bytes, n, cudaMemcpyDeviceToHost, c->st)); c->d2h += n;
+    CK(c, cudaMemcpyAsync(&h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+    if (consumed) *consumed = h_cnt;
+    return RBF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// frame stream
+// ------------------------------------------------------------------------------------------
+struct rbf_stream {
+    rbf_ctx* c;
+    uint32_t H, W, C, S, max_frames, max_pairs;
+    uint64_t npix, frame_bytes, frame_stride;
+    uint8_t* d_frames = nullptr;
+    size_t mask_stride_w = 0, pass_stride_w = 0;     // words per pair
+    uint32_t *d_mask = nullptr, *d_bits = nullptr, *d_wit = nullptr, *d_pass = nullptr, *d_dec = nullptr;
+    FrameJob* d_jobs = nullptr;
+    PairJob* d_pairs = nullptr;
+    uint32_t *d_prefix = nullptr, *d_ones = nullptr, *d_resid = nullptr, *d_wlen = nullptr;
+    // pinned host mirrors
+    FrameJob* h_jobs = nullptr;
+    PairJob* h_pairs = nullptr;
+    uint32_t *h_prefix = nullptr, *h_ones = nullptr, *h_resid = nullptr, *h_wlen = nullptr;
+    uint32_t last_pairs = 0;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool staged = false;
+    std::vector<rbf_mask_info> last_infos;
+};
+
+extern "C" void rbf_stream_destroy(rbf_stream* s) {
+    if (!s) return;
+    cudaSetDevice(s->c->device);
+    cudaFree(s->d_frames); cudaFree(s->d_mask); cudaFree(s->d_bits); cudaFree(s->d_wit); cudaFree(s->d_pass); cudaFree(s->d_dec);
+    cudaFree(s->d_jobs); cudaFree(s->d_pairs); cudaFree(s->d_prefix); cudaFree(s->d_ones); cudaFree(s->d_resid); cudaFree(s->d_wlen);
+    for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+    cudaFreeHost(s->h_jobs); cudaFreeHost(s->h_pairs); cudaFreeHost(s->h_prefix); cudaFreeHost(s->h_ones); cudaFreeHost(s->h_resid); cudaFreeHost(s->h_wlen);
+    delete s;
+}
+
+extern "C" int rbf_stream_create(rbf_ctx* c, uint32_t H, uint32_t W, uint32_t C, uint32_t S, uint32_t max_frames,
+                                 uint32_t max_pairs, rbf_stream** out) {
+    if (!c || !out) return set_err(c, RBF_ERR_INVALID, "rbf_stream_create: NULL");
+    if (!(S == 1 || S == 2) || !(C == 1 || C == 3) || H == 0 || W == 0 || max_frames < 2 || max_pairs < 1)
+        return set_err(c, RBF_ERR_INVALID, "unsupported frame format H=%u W=%u C=%u sample_bytes=%u", H, W, C, S);
+    const uint64_t npix = (uint64_t)H * W;
+    if (npix > 0xffffff00ULL) return set_err(c, RBF_ERR_INVALID, "frame too large");
+    CK(c, cudaSetDevice(c->device));
+    rbf_stream* s = new rbf_stream();
+    s->c = c; s->H = H; s->W = W; s->C = C; s->S = S; s->max_frames = max_frames; s->max_pairs = max_pairs;
+    s->npix = npix; s->frame_bytes = npix * C * S; s->frame_stride = align_up(s->frame_bytes + 64, 256);
+    s->mask_stride_w = bit_words_padded(npix);
+    s->pass_stride_w = pass_words(npix);
+    cudaError_t e = cudaSuccess;
+    auto dalloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    auto halloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMallocHost(p, bytes); };
+    dalloc((void**)&s->d_frames, s->frame_stride * max_frames);
+    dalloc((void**)&s->d_mask, s->mask_stride_w * 4 * max_pairs);
+    dalloc((void**)&s->d_bits, s->mask_stride_w * 4 * max_pairs);
+    dalloc((void**)&s->d_wit, s->mask_stride_w * 4 * max_pairs);
+    dalloc((void**)&s->d_pass, s->pass_stride_w * 4 * max_pairs);
+    dalloc((void**)&s->d_jobs, sizeof(FrameJob) * max_pairs);
+    dalloc((void**)&s->d_pairs, sizeof(PairJob) * max_pairs);
+    dalloc((void**)&s->d_prefix, 4 * ((size_t)max_pairs + 1));
+    dalloc((void**)&s->d_ones, 4 * (size_t)max_pairs);
+    dalloc((void**)&s->d_resid, 4 * (size_t)max_pairs);
+    dalloc((void**)&s->d_wlen, 4 * (size_t)max_pairs);
+    halloc((void**)&s->h_jobs, sizeof(FrameJob) * max_pairs);
+    halloc((void**)&s->h_pairs, sizeof(PairJob) * max_pairs);
+    halloc((void**)&s->h_prefix, 4 * ((size_t)max_pairs + 1));
+    halloc((void**)&s->h_ones, 4 * (size_t)max_pairs);
+    halloc((void**)&s->h_resid, 4 * (size_t)max_pairs);
+    halloc((void**)&s->h_wlen, 4 * (size_t)max_pairs);
+    if (e != cudaSuccess) {
+        rbf_stream_destroy(s);
+        return set_err(c, e == cudaErrorMemoryAllocation ? RBF_ERR_OOM : RBF_ERR_CUDA, "rbf_stream_create: %s", cudaGetErrorString(e));
+    }
+    for (auto& ev : s->ev) CK(c, cudaEventCreate(&ev));
+    CK(c, cudaMemsetAsync(s->d_mask, 0, s->mask_stride_w * 4 * max_pairs, c->st));   // zero padding once
+    CK(c, cudaStreamSynchronize(c->st));
+    *out = s;
+    return RBF_OK;
+}
+
+extern "C" int rbf_stream_upload(rbf_stream* s, uint32_t first, uint32_t count, const void* host) {
+    if (!s || !host) return set_err(s ? s->c : nullptr, RBF_ERR_INVALID, "rbf_stream_upload: NULL");
+    rbf_ctx* c = s->c;
+    if ((uint64_t)first + count > s->max_frames) return set_err(c, RBF_ERR_INVALID, "frames [%u,%u) exceed store of %u", first, first + count, s->max_frames);
+    CK(c, cudaMemcpy2DAsync(s->d_frames + (size_t)first * s->frame_stride, s->frame_stride, host, s->frame_bytes, s->frame_bytes,
+                            count, cudaMemcpyHostToDevice, c->st));
+    c->h2d += (int64_t)s->frame_bytes * count;
+    CK(c, cudaStreamSynchronize(c->st));
+    return RBF_OK;
+}
+extern "C" int rbf_stream_frame_ptr(rbf_stream* s, uint32_t frame, void** dptr) {
+    if (!s || !dptr || frame >= s->max_frames) return set_err(s ? s->c : nullptr, RBF_ERR_INVALID, "rbf_stream_frame_ptr: bad argument");
+    *dptr = s->d_frames + (size_t)frame * s->frame_stride;
+    return RBF_OK;
+}
+extern "C" int rbf_stream_bitmap_region(rbf_stream* s, void** dptr, uint64_t* stride) {
+    if (!s) return RBF_ERR_INVALID;
+    if (dptr) *dptr = s->d_bits;
+    if (stride) *stride = s->mask_stride_w * 4;
+    return RBF_OK;
+}
+
+// `diff > threshold` with integer diff and a Python float threshold (ivc:808)  ==  diff > floor(threshold)
+static int threshold_to_int(double thr) {
+    if (isnan(thr)) return 0x7fffffff;                 // every comparison with NaN is False
+    if (thr < -1.0) return -1;                         // diff >= -32768 only for uint16 wrap; handled below
+    if (thr > 1e9) return 0x7fffffff;
+    return (int)floor(thr);
+}
+
+static int stream_encode_async(rbf_stream* s, const uint32_t* prev_idx, const uint32_t* curr_idx, uint32_t pairs,
+                               double threshold, const rbf_seeds* sd, const double* kov, const uint64_t* lov) {
+    rbf_ctx* c = s->c;
+    const uint32_t n = (uint32_t)s->npix;
+    int thr_int = threshold_to_int(threshold);
+    if (s->S == 2 && threshold < -1.0) {               // int16 abs can be -32768 (ivc:801): keep exact floor
+        thr_int = threshold < -40000.0 ? -40000 : (int)floor(threshold);
+    }
+    for (uint32_t i = 0; i < pairs; i++) {
+        if (prev_idx[i] >= s->max_frames || curr_idx[i] >= s->max_frames)
+            return set_err(c, RBF_ERR_INVALID, "pair %u references a frame outside the store", i);
+        s->h_pairs[i].prev = s->d_frames + (size_t)prev_idx[i] * s->frame_stride;
+        s->h_pairs[i].curr = s->d_frames + (size_t)curr_idx[i] * s->frame_stride;
+        s->h_pairs[i].mask = s->d_mask + (size_t)i * s->mask_stride_w;
+    }
+    CK(c, cudaMemcpyAsync(s->d_pairs, s->h_pairs, sizeof(PairJob) * pairs, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemsetAsync(s->d_ones, 0, 4 * (size_t)pairs, c->st));
+    CK(c, cudaMemsetAsync(s->d_resid, 0, 4 * (size_t)pairs, c->st));
+    s->staged = false;
+    CK(c, cudaEventRecord(s->ev[0], c->st));
+    LAUNCH(c, launch_threshold(s->d_pairs, (int)pairs, n, (int)s->C, (int)s->S, thr_int, c->mask_mode, s->d_ones, s->d_resid, c->k1_variant,
+                               c->sm_count, c->st));
+    if (c->k1_variant == 1) c->launches++;              // tail kernel
+    CK(c, cudaEventRecord(s->ev[1], c->st));
+    CK(c, cudaMemcpyAsync(s->h_ones, s->d_ones, 4 * (size_t)pairs, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaMemcpyAsync(s->h_resid, s->d_resid, 4 * (size_t)pairs, cudaMemcpyDeviceToHost, c->st));
+    c->d2h += 8 * (int64_t)pairs;
+    CK(c, cudaStreamSynchronize(c->st));               // the one host round trip: (p, k, l, T) need libm's log2
+    s->last_infos.assign(pairs, rbf_mask_info());
+    const uint32_t ncent = (n + 99u) / 100u;
+    uint32_t total_cent = 0, coded_pairs = 0;
+    s->h_prefix[0] = 0;
+    for (uint32_t i = 0; i < pairs; i++) {
+        rbf_mask_info& in = s->last_infos[i];
+        memset(&in, 0, sizeof in);
+        in.n = n; in.ones = s->h_ones[i]; in.resid = s->h_resid[i];
+        double p, k; uint64_t l;
+        int coded = rbf_optimal_params(n, in.ones, &p, &k, &l);
+        in.p = p;
+        if (kov && kov[i] > 0.0 && !(p >= kPStar)) { k = kov[i]; l = lov ? lov[i] : 0; coded = !(l == 0 || l >= n); }
+        FrameJob& J = s->h_jobs[i];
+        memset(&J, 0, sizeof J);
+        J.n = n;
+        J.mask = s->d_mask + (size_t)i * s->mask_stride_w;
+        J.bits = s->d_bits + (size_t)i * s->mask_stride_w;
+        J.witness = s->d_wit + (size_t)i * s->mask_stride_w;
+        J.pass = s->d_pass + (size_t)i * s->pass_stride_w;
+        if (coded) {
+            job_set_filter(J, l, k, *sd);
+            in.k = k; in.l = l; in.floor_k = J.floor_k; in.act_T = J.act_T;
+            total_cent += ncent; coded_pairs++;
+        } else {
+            in.raw = 1;
+        }
+        s->h_prefix[i + 1] = total_cent;
+    }
+    s->last_pairs = pairs;
+    if (coded_pairs == 0 || c->k1_only) return RBF_OK;
+    CK(c, cudaMemcpyAsync(s->d_jobs, s->h_jobs, sizeof(FrameJob) * pairs, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(s->d_prefix, s->h_prefix, 4 * ((size_t)pairs + 1), cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemsetAsync(s->d_bits, 0, s->mask_stride_w * 4 * pairs, c->st));
+    CK(c, cudaMemsetAsync(s->d_wit, 0, s->mask_stride_w * 4 * pairs, c->st));
+    CK(c, cudaEventRecord(s->ev[2], c->st));
+    LAUNCH(c, launch_insert(s->d_jobs, (int)pairs, ncent, c->sm_count, c->st));
+    CK(c, cudaEventRecord(s->ev[3], c->st));
+    LAUNCH(c, launch_query(s->d_jobs, s->d_prefix, (int)pairs, total_cent, c->sm_count, c->query_smem_cap, c->st));
+    CK(c, cudaEventRecord(s->ev[4], c->st));
+    LAUNCH(c, launch_witness(s->d_jobs, (int)pairs, s->d_wlen, c->st));
+    CK(c, cudaEventRecord(s->ev[5], c->st));
+    s->staged = true;
+    CK(c, cudaMemcpyAsync(s->h_wlen, s->d_wlen, 4 * (size_t)pairs, cudaMemcpyDeviceToHost, c->st));
+    c->d2h += 4 * (int64_t)pairs;
+    return RBF_OK;
+}
+
+extern "C" int rbf_stream_encode(rbf_stream* s, const uint32_t* prev_idx, const uint32_t* curr_idx, uint32_t pairs,
+                                 double threshold, const rbf_seeds* sd, const double* kov, const uint64_t* lov,
+                                 rbf_mask_info* infos) {
+    if (!s || !prev_idx || !curr_idx || !sd) return set_err(s ? s->c : nullptr, RBF_ERR_INVALID, "rbf_stream_encode: NULL");
+    rbf_ctx* c = s->c;
+    if (pairs == 0 || pairs > s->max_pairs) return set_err(c, RBF_ERR_INVALID, "pairs = %u outside [1, %u]", pairs, s->max_pairs);
+    CK(c, cudaSetDevice(c->device));
+    int rc = stream_encode_async(s, prev_idx, curr_idx, pairs, threshold, sd, kov, lov);
+    if (rc) return rc;
+    CK(c, cudaStreamSynchronize(c->st));
+    for (uint32_t i = 0; i < pairs; i++) {
+        if (!s->last_infos[i].raw) s->last_infos[i].wlen = s->h_wlen[i];
+        if (infos) infos[i] = s->last_infos[i];
+    }
+    return RBF_OK;
+}
+
+extern "C" int rbf_stream_stage_ms(rbf_stream* s, double out[5]) {
+    if (!s || !out) return RBF_ERR_INVALID;
+    rbf_ctx* c = s->c;
+    if (!s->staged) return set_err(c, RBF_ERR_STATE, "no fully staged encode has run");
+    CK(c, cudaEventSynchronize(s->ev[5]));
+    for (int i = 0; i < 5; i++) { float f = 0; CK(c, cudaEventElapsedTime(&f, s->ev[i], s->ev[i + 1])); out[i] = f; }
+    return RBF_OK;
+}
+
+extern "C" int rbf_stream_fetch(rbf_stream* s, uint32_t pair, uint8_t* bitmap, uint8_t* witness, uint8_t* mask_little) {
+    if (!s) return RBF_ERR_INVALID;
+    rbf_ctx* c = s->c;
+    if (pair >= s->last_pairs) return set_err(c, RBF_ERR_INVALID, "pair %u was not encoded", pair);
+    const rbf_mask_info& in = s->last_infos[pair];
+    if (bitmap && !in.raw) { size_t nb = (in.l + 7) / 8; CK(c, cudaMemcpyAsync(bitmap, s->d_bits + (size_t)pair * s->mask_stride_w, nb, cudaMemcpyDeviceToHost, c->st)); c->d2h += nb; }
+    if (witness && !in.raw && in.wlen) { size_t nb = (in.wlen + 7) / 8; CK(c, cudaMemcpyAsync(witness, s->d_wit + (size_t)pair * s->mask_stride_w, nb, cudaMemcpyDeviceToHost, c->st)); c->d2h += nb; }
+    if (mask_little) { size_t nb = (s->npix + 7) / 8; CK(c, cudaMemcpyAsync(mask_little, s->d_mask + (size_t)pair * s->mask_stride_w, nb, cudaMemcpyDeviceToHost, c->st)); c->d2h += nb; }
+    CK(c, cudaStreamSynchronize(c->st));
+    return RBF_OK;
+}
+
+extern "C" int rbf_stream_encode_host(rbf_stream* s, const void* host_frames, uint32_t nframes, double threshold,
+                                      const rbf_seeds* sd, rbf_mask_info* infos, uint8_t* bitmaps, uint64_t bitmap_slot,
+                                      uint8_t* witness, uint64_t witness_slot) {
+    if (!s || !host_frames || !sd || nframes < 2) return set_err(s ? s->c : nullptr, RBF_ERR_INVALID, "rbf_stream_encode_host: bad argument");
+    rbf_ctx* c = s->c;
+    const uint32_t pairs = nframes - 1;
+    if (nframes > s->max_frames || pairs > s->max_pairs) return set_err(c, RBF_ERR_INVALID, "stream too small for %u frames", nframes);
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaMemcpy2DAsync(s->d_frames, s->frame_stride, host_frames, s->frame_bytes, s->frame_bytes, nframes,
+                            cudaMemcpyHostToDevice, c->st));
+    c->h2d += (int64_t)s->frame_bytes * nframes;
+    std::vector<uint32_t> pi(pairs), ci(pairs);
+    for (uint32_t i = 0; i < pairs; i++) { pi[i] = i; ci[i] = i + 1; }
+    int rc = stream_encode_async(s, pi.data(), ci.data(), pairs, threshold, sd, nullptr, nullptr);
+    if (rc) return rc;
+    const size_t stride = s->mask_stride_w * 4;
+    if (bitmaps && bitmap_slot) {
+        const size_t w = bitmap_slot < stride ? bitmap_slot : stride;
+        CK(c, cudaMemcpy2DAsync(bitmaps, bitmap_slot, s->d_bits, stride, w, pairs, cudaMemcpyDeviceToHost, c->st));
+        c->d2h += (int64_t)w * pairs;
+    }
+    if (witness && witness_slot) {
+        const size_t w = witness_slot < stride ? witness_slot : stride;
+        CK(c, cudaMemcpy2DAsync(witness, witness_slot, s->d_wit, stride, w, pairs, cudaMemcpyDeviceToHost, c->st));
+        c->d2h += (int64_t)w * pairs;
+    }
+    CK(c, cudaStreamSynchronize(c->st));
+    for (uint32_t i = 0; i < pairs; i++) {
+        if (!s->last_infos[i].raw) s->last_infos[i].wlen = s->h_wlen[i];
+        if (infos) infos[i] = s->last_infos[i];
+    }
+    return RBF_OK;
+}
+
+extern "C" int rbf_stream_decode_verify(rbf_stream* s, uint32_t pairs, uint64_t* mismatches) {
+    if (!s || !mismatches) return set_err(s ? s->c : nullptr, RBF_ERR_INVALID, "rbf_stream_decode_verify: NULL");
+    rbf_ctx* c = s->c;
+    if (pairs == 0 || pairs > s->last_pairs) return set_err(c, RBF_ERR_INVALID, "only %u pairs were encoded", s->last_pairs);
+    CK(c, cudaSetDevice(c->device));
+    const size_t stride_w = s->mask_stride_w;
+    if (!s->d_dec) CK(c, cudaMalloc((void**)&s->d_dec, stride_w * 4 * s->max_pairs));
+    CK(c, cudaMemsetAsync(s->d_dec, 0, stride_w * 4 * pairs, c->st));
+    // bitmap and witness sit in packbits order after K3b; the kernels work LSB-first
+    LAUNCH(c, launch_bitrev(s->d_bits, stride_w * pairs, c->st));
+    LAUNCH(c, launch_bitrev(s->d_wit, stride_w * pairs, c->st));
+    for (uint32_t i = 0; i < pairs; i++) {
+        FrameJob& J = s->h_jobs[i];
+        J.out_mask = s->d_dec + (size_t)i * stride_w;
+        J.wlen_in = (uint32_t)s->last_infos[i].wlen;
+    }
+    CK(c, cudaMemcpyAsync(s->d_jobs, s->h_jobs, sizeof(FrameJob) * pairs, cudaMemcpyHostToDevice, c->st));
+    const uint32_t total_cent = s->h_prefix[pairs];
+    LAUNCH(c, launch_query(s->d_jobs, s->d_prefix, (int)pairs, total_cent, c->sm_count, c->query_smem_cap, c->st));
+    LAUNCH(c, launch_expand(s->d_jobs, (int)pairs, s->d_wlen, c->st));
+    void* d_cnt; int rc;
+    if ((rc = scratch_get(c, 7, 4 * (size_t)pairs + 4096, &d_cnt))) return rc;
+    CK(c, cudaMemsetAsync(d_cnt, 0, 4 * (size_t)pairs, c->st));
+    LAUNCH(c, launch_count_diff(s->d_mask, s->d_dec, stride_w, (s->npix + 31) / 32, (int)pairs, (uint32_t*)d_cnt, c->st));
+    LAUNCH(c, launch_bitrev(s->d_bits, stride_w * pairs, c->st));
+    LAUNCH(c, launch_bitrev(s->d_wit, stride_w * pairs, c->st));
+    std::vector<uint32_t> h(pairs);
+    CK(c, cudaMemcpyAsync(h.data(), d_cnt, 4 * (size_t)pairs, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+    for (uint32_t i = 0; i < pairs; i++) mismatches[i] = s->last_infos[i].raw ? 0 : h[i];
+    return RBF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// NCCL (dlopen'ed so that single-GPU use needs no NCCL at all)
+// ------------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } nccl_uid;
+typedef int (*fn_GetUniqueId)(nccl_uid*);
+typedef int (*fn_CommInitRank)(void**, int, nccl_uid, int);
+typedef int (*fn_AllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*fn_CommDestroy)(void*);
+typedef const char* (*fn_GetErrorString)(int);
+
+static void* g_nccl = nullptr;
+static void* nccl_handle() {
+    if (!g_nccl) {
+        g_nccl = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!g_nccl) g_nccl = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    }
+    return g_nccl;
+}
+extern "C" int rbf_nccl_unique_id(uint8_t id_out[128]) {
+    void* h = nccl_handle();
+    if (!h) return set_err(nullptr, RBF_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+    fn_GetUniqueId f = (fn_GetUniqueId)dlsym(h, "ncclGetUniqueId");
+    if (!f) return set_err(nullptr, RBF_ERR_NCCL, "ncclGetUniqueId not found");
+    nccl_uid u;
+    int r = f(&u);
+    if (r) return set_err(nullptr, RBF_ERR_NCCL, "ncclGetUniqueId failed: %d", r);
+    memcpy(id_out, u.internal, 128);
+    return RBF_OK;
+}
+extern "C" int rbf_nccl_init(rbf_ctx* c, const uint8_t id[128], int rank, int nranks) {
+    if (!c || !id) return set_err(c, RBF_ERR_INVALID, "rbf_nccl_init: NULL");
+    void* h = nccl_handle();
+    if (!h) return set_err(c, RBF_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+    fn_CommInitRank f = (fn_CommInitRank)dlsym(h, "ncclCommInitRank");
+    if (!f) return set_err(c, RBF_ERR_NCCL, "ncclCommInitRank not found");
+    CK(c, cudaSetDevice(c->device));
+    nccl_uid u;
+    memcpy(u.internal, id, 128);
+    void* comm = nullptr;
+    int r = f(&comm, nranks, u, rank);
+    if (r) {
+        fn_GetErrorString es = (fn_GetErrorString)dlsym(h, "ncclGetErrorString");
+        return set_err(c, RBF_ERR_NCCL, "ncclCommInitRank failed: %s", es ? es(r) : "?");
+    }
+    c->nccl_lib = h; c->nccl_comm = comm; c->rank = rank; c->nranks = nranks;
+    return RBF_OK;
+}
+extern "C" int rbf_nccl_allgather(rbf_ctx* c, const void* d_send, void* d_recv, uint64_t bytes_per_rank) {
+    if (!c || !c->nccl_comm) return set_err(c, RBF_ERR_STATE, "rbf_nccl_allgather: communicator not initialised");
+    fn_AllGather f = (fn_AllGather)dlsym(c->nccl_lib, "ncclAllGather");
+    if (!f) return set_err(c, RBF_ERR_NCCL, "ncclAllGather not found");
+    int r = f(d_send, d_recv, (size_t)bytes_per_rank, /*ncclUint8*/ 1, c->nccl_comm, c->st);
+    if (r) {
+        fn_GetErrorString es = (fn_GetErrorString)dlsym(c->nccl_lib, "ncclGetErrorString");
+        return set_err(c, RBF_ERR_NCCL, "ncclAllGather failed: %s", es ? es(r) : "?");
+    }
+    c->launches++;
+    return RBF_OK;
+}
+extern "C" int rbf_stream_allgather_bitmaps(rbf_stream* s, uint32_t pairs, uint64_t slot_bytes, void* d_send, void* d_recv) {
+    if (!s || !d_send || !d_recv) return set_err(s ? s->c : nullptr, RBF_ERR_INVALID, "rbf_stream_allgather_bitmaps: NULL");
+    rbf_ctx* c = s->c;
+    const size_t stride = s->mask_stride_w * 4;
+    if (slot_bytes == 0 || slot_bytes > stride || pairs > s->max_pairs) return set_err(c, RBF_ERR_INVALID, "bad slot/pairs");
+    CK(c, cudaMemcpy2DAsync(d_send, slot_bytes, s->d_bits, stride, slot_bytes, pairs, cudaMemcpyDeviceToDevice, c->st));
+    return rbf_nccl_allgather(c, d_send, d_recv, slot_bytes * pairs);
+}
+extern "C" int rbf_nccl_destroy(rbf_ctx* c) {
+    if (!c) return RBF_ERR_INVALID;
+    if (c->nccl_comm && c->nccl_lib) {
+        fn_CommDestroy f = (fn_CommDestroy)dlsym(c->nccl_lib, "ncclCommDestroy");
+        if (f) f(c->nccl_comm);
+    }
+    c->nccl_comm = nullptr;
+    return RBF_OK;
+}

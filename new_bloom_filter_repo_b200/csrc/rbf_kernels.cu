@@ -1,0 +1,870 @@
+// rbf_kernels.cu -- hand-written sm_100a kernels of the rational-Bloom hot path.
+//
+//   K1  k_threshold      |Y_prev - Y_curr| > thr  -> packed mask + ones count      (ivc:788-808, ivc:211)
+//   K2  k_insert         insert every set position into the frame's Bloom filter    (ivc:235-237, ivc:99-114)
+//   K3  k_query          Bloom test of ALL n positions -> pass mask                 (ivc:245-253, ivc:116-138)
+//   K3b k_witness        ordered witness = mask bits at passing positions           (ivc:253)
+//   K4b k_expand         decode: out[i] = witness[rank(i)] for passing i            (ivc:299-304)
+//
+// The Bloom bit array of the frame being queried is staged into shared memory with
+// cp.async.bulk (TMA bulk copy, mbarrier complete_tx); whatever exceeds the 227 KB of a
+// CTA is probed through L2.  Integer hashing / bit tests only: no tensor cores.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rbf_kernels.cuh"
+
+namespace rbf {
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + bulk async copy (TMA), cache-hinted loads
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {   // read-once frame data: do not pollute L1
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// 100-bit helpers (a "century" of positions)
+// ------------------------------------------------------------------------------------------
+struct Bits128 {
+    uint64_t lo, hi;
+};
+
+// bits [100c, 100c+nvalid) of a naturally packed bit array (buffer padded by >= 16 B)
+__device__ __forceinline__ Bits128 load_bits100(const uint32_t* __restrict__ base, uint32_t c, uint32_t nvalid) {
+    uint64_t off = 100ull * c;
+    uint32_t w = (uint32_t)(off >> 5), sh = (uint32_t)off & 31u;
+    uint32_t a0 = __ldg(base + w), a1 = __ldg(base + w + 1), a2 = __ldg(base + w + 2), a3 = __ldg(base + w + 3);
+    uint32_t b0 = __funnelshift_r(a0, a1, sh), b1 = __funnelshift_r(a1, a2, sh), b2 = __funnelshift_r(a2, a3, sh),
+             b3 = a3 >> sh;
+    Bits128 r;
+    r.lo = (uint64_t)b0 | ((uint64_t)b1 << 32);
+    r.hi = (uint64_t)b2 | ((uint64_t)b3 << 32);
+    if (nvalid >= 64) {
+        r.hi &= (1ull << (nvalid - 64)) - 1ull;      // nvalid <= 100
+    } else {
+        r.hi = 0;
+        r.lo &= (1ull << nvalid) - 1ull;              // nvalid < 64
+    }
+    return r;
+}
+
+// OR a (<=128-bit) value into a zero-initialised bit stream at an arbitrary bit offset
+__device__ __forceinline__ void or_bits128(uint32_t* __restrict__ W, uint64_t bitoff, uint64_t lo, uint64_t hi) {
+    uint32_t w = (uint32_t)(bitoff >> 5), sh = (uint32_t)bitoff & 31u;
+    uint32_t s0 = (uint32_t)lo, s1 = (uint32_t)(lo >> 32), s2 = (uint32_t)hi, s3 = (uint32_t)(hi >> 32);
+    uint32_t o0 = s0 << sh, o1 = __funnelshift_l(s0, s1, sh), o2 = __funnelshift_l(s1, s2, sh),
+             o3 = __funnelshift_l(s2, s3, sh), o4 = __funnelshift_l(s3, 0u, sh);
+    if (o0) atomicOr(W + w, o0);
+    if (o1) atomicOr(W + w + 1, o1);
+    if (o2) atomicOr(W + w + 2, o2);
+    if (o3) atomicOr(W + w + 3, o3);
+    if (o4) atomicOr(W + w + 4, o4);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: threshold + popcount.  One thread = 32 consecutive pixels = one mask word; the pixel
+// bytes are read with 128-bit streaming loads (2*PB of them per frame, all issued up front).
+// PB = bytes per pixel (channels * sample bytes), S = sample bytes; Y is the first sample.
+// ------------------------------------------------------------------------------------------
+template <int PB, int S>
+__device__ __forceinline__ int absdiff_sample(uint32_t a, uint32_t b) {
+    if (S == 1) {
+        int d = (int)a - (int)b;
+        return d < 0 ? -d : d;
+    } else {                                           // numpy int16 wrap-around (ivc:801)
+        int16_t x = (int16_t)(uint16_t)a, y = (int16_t)(uint16_t)b;
+        int16_t d = (int16_t)(x - y);
+        int16_t ad = (int16_t)(d < 0 ? -d : d);      // abs(-32768) stays -32768
+        return (int)ad;
+    }
+}
+
+template <int PB, int S>
+__global__ void __launch_bounds__(256) k_threshold(const PairJob* __restrict__ pairs, uint32_t npix, int thr, int any_mode,
+                                                   uint32_t* __restrict__ ones, uint32_t* __restrict__ resid) {
+    const PairJob pj = pairs[blockIdx.y];
+    const uint32_t nwords = (npix + 31u) >> 5;
+    uint32_t cnt_ones = 0, cnt_res = 0;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += gridDim.x * blockDim.x) {
+        const uint32_t px0 = w << 5;
+        uint32_t m = 0, r = 0;
+        if (px0 + 32u <= npix) {
+            constexpr int NV = 2 * PB;                 // uint4 per 32 pixels
+            constexpr int HV = (NV > 6) ? NV / 2 : NV; // cap registers: at most 6 uint4 per frame in flight
+            constexpr int HALVES = NV / HV;
+            constexpr int PXH = 32 / HALVES;
+#pragma unroll
+            for (int hf = 0; hf < HALVES; hf++) {
+                const uint4* pa = reinterpret_cast<const uint4*>(pj.prev + (size_t)(px0 + hf * PXH) * PB);
+                const uint4* pb = reinterpret_cast<const uint4*>(pj.curr + (size_t)(px0 + hf * PXH) * PB);
+                uint32_t A[4 * HV], B[4 * HV];
+#pragma unroll
+                for (int j = 0; j < HV; j++) {
+                    uint4 va = ldg_stream(pa + j);
+                    A[4 * j] = va.x; A[4 * j + 1] = va.y; A[4 * j + 2] = va.z; A[4 * j + 3] = va.w;
+                }
+#pragma unroll
+                for (int j = 0; j < HV; j++) {
+                    uint4 vb = ldg_stream(pb + j);
+                    B[4 * j] = vb.x; B[4 * j + 1] = vb.y; B[4 * j + 2] = vb.z; B[4 * j + 3] = vb.w;
+                }
+#pragma unroll
+                for (int k = 0; k < PXH; k++) {
+                    const int o = k * PB;              // byte offset of the pixel (compile-time)
+                    uint32_t ya, yb;
+                    if (S == 1) {
+                        ya = (A[o >> 2] >> (8 * (o & 3))) & 0xffu;
+                        yb = (B[o >> 2] >> (8 * (o & 3))) & 0xffu;
+                    } else {
+                        ya = (A[o >> 2] >> (8 * (o & 3))) & 0xffffu;
+                        yb = (B[o >> 2] >> (8 * (o & 3))) & 0xffffu;
+                    }
+                    uint32_t anyd = 0;                 // any byte of the pixel differs
+#pragma unroll
+                    for (int q = 0; q < PB; q++) {
+                        const int oq = o + q;
+                        anyd |= ((A[oq >> 2] ^ B[oq >> 2]) >> (8 * (oq & 3))) & 0xffu;
+                    }
+                    const uint32_t bit = ((absdiff_sample<PB, S>(ya, yb) > thr) || (any_mode && anyd != 0u)) ? 1u : 0u;
+                    m |= bit << (hf * PXH + k);
+                    r |= ((anyd != 0u && bit == 0u) ? 1u : 0u) << (hf * PXH + k);
+                }
+            }
+        } else {                                        // ragged last word: scalar loads
+            for (uint32_t k = 0; k < 32u && px0 + k < npix; k++) {
+                const uint8_t* a = pj.prev + (size_t)(px0 + k) * PB;
+                const uint8_t* b = pj.curr + (size_t)(px0 + k) * PB;
+                uint32_t ya = a[0], yb = b[0];
+                if (S == 2) { ya |= (uint32_t)a[1] << 8; yb |= (uint32_t)b[1] << 8; }
+                uint32_t anyd = 0;
+                for (int q = 0; q < PB; q++) anyd |= (uint32_t)(a[q] ^ b[q]);
+                const uint32_t bit = ((absdiff_sample<PB, S>(ya, yb) > thr) || (any_mode && anyd != 0u)) ? 1u : 0u;
+                m |= bit << k;
+                r |= ((anyd != 0u && bit == 0u) ? 1u : 0u) << k;
+            }
+        }
+        pj.mask[w] = m;
+        cnt_ones += __popc(m);
+        cnt_res += __popc(r);
+    }
+    // block reduction -> one atomic per block
+    __shared__ uint32_t s_o[8], s_r[8];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        cnt_ones += __shfl_xor_sync(0xffffffffu, cnt_ones, d);
+        cnt_res += __shfl_xor_sync(0xffffffffu, cnt_res, d);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_o[warp] = cnt_ones; s_r[warp] = cnt_res; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t to = 0, tr = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) { to += s_o[i]; tr += s_r[i]; }
+        if (to) atomicAdd(ones + blockIdx.y, to);
+        if (tr) atomicAdd(resid + blockIdx.y, tr);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 (TMA variant): persistent CTAs, 4-stage mbarrier ring, one elected thread issues
+// cp.async.bulk copies of a 2 x 12 KB tile (prev, curr); consumers read the Y bytes from
+// shared memory conflict-free (lane stride = PB bytes) and ballot the mask words directly.
+// ------------------------------------------------------------------------------------------
+constexpr int TMA_STAGES = 4;
+constexpr int TMA_TILE_BYTES = 12288;                  // per frame per stage (4096 px at 3 B/px)
+constexpr int TMA_THREADS = 256;
+
+template <int PB, int S>
+__global__ void __launch_bounds__(TMA_THREADS) k_threshold_tma(const PairJob* __restrict__ pairs, int F, uint32_t npix,
+                                                               int thr, int any_mode, uint32_t* __restrict__ ones,
+                                                               uint32_t* __restrict__ resid) {
+    constexpr uint32_t TP = TMA_TILE_BYTES / PB;       // pixels per tile (multiple of 32*8)
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full[TMA_STAGES];
+    uint8_t* bufA = smem;                               // [STAGES][TILE]
+    uint8_t* bufB = smem + TMA_STAGES * TMA_TILE_BYTES;
+    const uint32_t full_tiles = npix / TP;              // tiles fully inside a frame (bulk copy needs 16 B multiples)
+    const uint32_t tiles_per_frame = full_tiles;
+    const uint64_t total = (uint64_t)tiles_per_frame * (uint64_t)F;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NWARP = TMA_THREADS / 32;
+    constexpr uint32_t WPW = TP / 32 / NWARP;           // mask words per warp per tile
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TMA_STAGES; s++) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](uint64_t t, int slot) {
+        const uint32_t f = (uint32_t)(t / tiles_per_frame), ti = (uint32_t)(t % tiles_per_frame);
+        const PairJob pj = pairs[f];
+        mbar_expect_tx(&full[slot], 2 * TMA_TILE_BYTES);
+        bulk_g2s(bufA + slot * TMA_TILE_BYTES, pj.prev + (size_t)ti * TMA_TILE_BYTES, TMA_TILE_BYTES, &full[slot]);
+        bulk_g2s(bufB + slot * TMA_TILE_BYTES, pj.curr + (size_t)ti * TMA_TILE_BYTES, TMA_TILE_BYTES, &full[slot]);
+    };
+
+    // prologue
+    uint64_t t0 = blockIdx.x;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TMA_STAGES - 1; s++) {
+            uint64_t t = t0 + (uint64_t)s * gridDim.x;
+            if (t < total) issue(t, s);
+        }
+    }
+    uint32_t it = 0;
+    for (uint64_t t = t0; t < total; t += gridDim.x, it++) {
+        const int slot = it % TMA_STAGES;
+        const uint32_t parity = (it / TMA_STAGES) & 1u;
+        if (threadIdx.x == 0) {                         // refill the slot freed by the previous iteration
+            uint64_t tn = t + (uint64_t)(TMA_STAGES - 1) * gridDim.x;
+            if (tn < total) { fence_proxy_async(); issue(tn, (it + TMA_STAGES - 1) % TMA_STAGES); }
+        }
+        mbar_wait(&full[slot], parity);
+        const uint32_t f = (uint32_t)(t / tiles_per_frame), ti = (uint32_t)(t % tiles_per_frame);
+        const uint8_t* a = bufA + slot * TMA_TILE_BYTES;
+        const uint8_t* b = bufB + slot * TMA_TILE_BYTES;
+        uint32_t myword = 0, c_o = 0, c_r = 0;
+#pragma unroll 4
+        for (uint32_t k = 0; k < WPW; k++) {
+            const uint32_t px = (warp * WPW + k) * 32u + lane;
+            const uint8_t* pa = a + px * PB;
+            const uint8_t* pb = b + px * PB;
+            uint32_t ya, yb, anyd = 0;
+            if (S == 1) { ya = pa[0]; yb = pb[0]; }
+            else { ya = *reinterpret_cast<const uint16_t*>(pa); yb = *reinterpret_cast<const uint16_t*>(pb); }
+#pragma unroll
+            for (int q = 0; q < PB; q += S) {
+                if (S == 1) anyd |= (uint32_t)(pa[q] ^ pb[q]);
+                else anyd |= (uint32_t)(*reinterpret_cast<const uint16_t*>(pa + q) ^ *reinterpret_cast<const uint16_t*>(pb + q));
+            }
+            const bool bit = (absdiff_sample<PB, S>(ya, yb) > thr) || (any_mode && anyd != 0u);
+            const uint32_t bm = __ballot_sync(0xffffffffu, bit);
+            const uint32_t br = __ballot_sync(0xffffffffu, (!bit) && anyd != 0u);
+            if (lane == (int)k) myword = bm;
+            c_o += __popc(bm); c_r += __popc(br);      // identical in every lane
+        }
+        if (lane < (int)WPW) pairs[f].mask[(size_t)ti * (TP / 32) + warp * WPW + lane] = myword;
+        if (lane == 0) {
+            if (c_o) atomicAdd(ones + f, c_o);
+            if (c_r) atomicAdd(resid + f, c_r);
+        }
+        __syncthreads();                                // slot may be refilled next iteration
+    }
+}
+
+// remainder of each frame after the last full TMA tile: same maths with guarded scalar loads
+template <int PB, int S>
+__global__ void __launch_bounds__(256) k_threshold_tail(const PairJob* __restrict__ pairs, uint32_t npix, uint32_t px_begin,
+                                                        int thr, int any_mode, uint32_t* __restrict__ ones, uint32_t* __restrict__ resid) {
+    const PairJob pj = pairs[blockIdx.y];
+    const uint32_t w0 = px_begin >> 5, nwords = (npix + 31u) >> 5;
+    for (uint32_t w = w0 + blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += gridDim.x * blockDim.x) {
+        uint32_t m = 0, r = 0;
+        for (uint32_t k = 0; k < 32u && (w << 5) + k < npix; k++) {
+            const uint8_t* a = pj.prev + (size_t)((w << 5) + k) * PB;
+            const uint8_t* b = pj.curr + (size_t)((w << 5) + k) * PB;
+            uint32_t ya = a[0], yb = b[0];
+            if (S == 2) { ya |= (uint32_t)a[1] << 8; yb |= (uint32_t)b[1] << 8; }
+            uint32_t anyd = 0;
+            for (int q = 0; q < PB; q++) anyd |= (uint32_t)(a[q] ^ b[q]);
+            const uint32_t bit = ((absdiff_sample<PB, S>(ya, yb) > thr) || (any_mode && anyd != 0u)) ? 1u : 0u;
+            m |= bit << k;
+            r |= ((anyd != 0u && bit == 0u) ? 1u : 0u) << k;
+        }
+        pj.mask[w] = m;
+        if (m) atomicAdd(ones + blockIdx.y, __popc(m));
+        if (r) atomicAdd(resid + blockIdx.y, __popc(r));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-filter constants kept in registers / shared memory
+// ------------------------------------------------------------------------------------------
+struct FilterK {
+    FastMod fm;
+    uint64_t T, s1, s2, sA;
+    uint32_t fk, has_act;
+};
+__device__ __forceinline__ FilterK filter_consts(const FrameJob& J) {
+    FilterK k;
+    k.fm = J.fm; k.T = J.act_T; k.s1 = J.seed1; k.s2 = J.seed2; k.sA = J.seedA; k.fk = J.floor_k; k.has_act = J.has_act;
+    return k;
+}
+
+// add_index on a global, LSB-first bit array (ivc:99-114) given the three hashes
+__device__ __forceinline__ void insert_hashes(uint32_t* __restrict__ bits, const FilterK& K, uint64_t h1, uint64_t h2,
+                                              uint64_t hA) {
+    uint32_t idx = mod_u64(h1, K.fm);
+    const uint32_t step = mod_u64(h2, K.fm);
+    for (uint32_t i = 0; i < K.fk; i++) {
+        atomicOr(bits + (idx >> 5), 1u << (idx & 31u));
+        idx = addmod(idx, step, K.fm.m);
+    }
+    if (K.has_act && hA < K.T) atomicOr(bits + (idx >> 5), 1u << (idx & 31u));
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: insert.  One thread owns a century (100 positions); the few set positions of the mask
+// are hashed with the shared century/decade prefix states and OR-ed into the bit array in L2.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_insert(const FrameJob* __restrict__ jobs) {
+    const FrameJob& J = jobs[blockIdx.y];
+    if (J.l == 0) return;
+    const FilterK K = filter_consts(J);
+    const uint32_t ncent = (J.n + 99u) / 100u;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < ncent; c += gridDim.x * blockDim.x) {
+        const uint32_t nvalid = min(100u, J.n - 100u * c);
+        Bits128 mb = load_bits100(J.mask, c, nvalid);
+        if ((mb.lo | mb.hi) == 0ull) continue;
+        const Century cen = make_century(c);
+        const uint64_t C1 = century_state(cen, K.s1), C2 = century_state(cen, K.s2), CA = century_state(cen, K.sA);
+        for (int half = 0; half < 2; half++) {
+            uint64_t v = half ? mb.hi : mb.lo;
+            while (v) {
+                const uint32_t pos = (uint32_t)(__ffsll((long long)v) - 1) + 64u * half;
+                v &= v - 1ull;
+                const uint32_t x = pos / 10u, y = pos - 10u * x;
+                const uint64_t h1 = finish(cen.kind, decade_state(cen, C1, K.s1, x), K.s1, y);
+                const uint64_t h2 = finish(cen.kind, decade_state(cen, C2, K.s2, x), K.s2, y);
+                const uint64_t hA = K.has_act ? finish(cen.kind, decade_state(cen, CA, K.sA, x), K.sA, y) : 0ull;
+                insert_hashes(J.bits, K, h1, h2, hA);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: query.  Persistent CTAs split the batch's centuries evenly; for every frame segment the
+// CTA stages the frame's bit array into shared memory with TMA bulk copies (the tail that does
+// not fit is probed through L2) and tests all positions.  Output: pass mask, 128 bits/century.
+// ------------------------------------------------------------------------------------------
+constexpr int QT = 512;
+
+struct BitView {
+    const uint32_t* sm;      // shared-memory copy of words [0, sm_words)
+    const uint32_t* gl;      // whole array in global memory
+    uint32_t sm_words;
+};
+__device__ __forceinline__ uint32_t test_bit(const BitView& bv, uint32_t idx) {
+    const uint32_t w = idx >> 5;
+    const uint32_t word = (w < bv.sm_words) ? bv.sm[w] : __ldg(bv.gl + w);
+    return (word >> (idx & 31u)) & 1u;
+}
+
+// check_index (ivc:116-138) for the position with decade states D1, D2, DA and units digit y
+__device__ __forceinline__ uint32_t check_one(const BitView& bv, const FilterK& K, int kind, uint64_t D1, uint64_t D2,
+                                              uint64_t DA, uint32_t y) {
+    uint32_t idx = mod_u64(finish(kind, D1, K.s1, y), K.fm);
+    uint32_t ok = 1u;
+    if (K.fk >= 1u) ok = test_bit(bv, idx);
+    if (ok && (K.fk >= 2u || K.has_act)) {
+        const uint32_t step = mod_u64(finish(kind, D2, K.s2, y), K.fm);
+        for (uint32_t i = 1; i < K.fk && ok; i++) {
+            idx = addmod(idx, step, K.fm.m);
+            ok = test_bit(bv, idx);
+        }
+        if (ok && K.has_act && finish(kind, DA, K.sA, y) < K.T) {
+            if (K.fk >= 1u) idx = addmod(idx, step, K.fm.m);
+            ok = test_bit(bv, idx);
+        }
+    }
+    return ok;
+}
+
+__device__ __forceinline__ Bits128 query_century(const BitView& bv, const FilterK& K, uint32_t c, uint32_t nvalid) {
+    const Century cen = make_century(c);
+    const uint64_t C1 = century_state(cen, K.s1), C2 = century_state(cen, K.s2), CA = century_state(cen, K.sA);
+    Bits128 res; res.lo = 0; res.hi = 0;
+#pragma unroll 1
+    for (uint32_t x = 0; x < 10u; x++) {
+        const uint64_t D1 = decade_state(cen, C1, K.s1, x), D2 = decade_state(cen, C2, K.s2, x),
+                       DA = decade_state(cen, CA, K.sA, x);
+        uint32_t dres = 0;
+#pragma unroll
+        for (uint32_t y = 0; y < 10u; y++) dres |= check_one(bv, K, cen.kind, D1, D2, DA, y) << y;
+        const uint32_t p0 = 10u * x;
+        if (p0 < 64u) {
+            res.lo |= (uint64_t)dres << p0;
+            if (p0 > 54u) res.hi |= (uint64_t)dres >> (64u - p0);
+        } else {
+            res.hi |= (uint64_t)dres << (p0 - 64u);
+        }
+    }
+    if (nvalid < 100u) {
+        if (nvalid >= 64u) res.hi &= (1ull << (nvalid - 64u)) - 1ull;
+        else { res.hi = 0; res.lo &= (1ull << nvalid) - 1ull; }
+    }
+    return res;
+}
+
+__global__ void __launch_bounds__(QT) k_query(const FrameJob* __restrict__ jobs, const uint32_t* __restrict__ cent_prefix,
+                                              int F, uint32_t smem_words_cap) {
+    extern __shared__ __align__(128) uint32_t sbits[];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t total = cent_prefix[F];
+    const uint32_t lo = (uint32_t)(((uint64_t)total * blockIdx.x) / gridDim.x);
+    const uint32_t hi = (uint32_t)(((uint64_t)total * (blockIdx.x + 1)) / gridDim.x);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (lo >= hi) return;
+    // first frame with cent_prefix[f+1] > lo
+    int f = 0;
+    { int a = 0, b = F; while (a < b) { int m = (a + b) >> 1; if (cent_prefix[m + 1] > lo) b = m; else a = m + 1; } f = a; }
+    uint32_t parity = 0, g = lo;
+    while (g < hi) {
+        while (cent_prefix[f + 1] <= g) f++;
+        const FrameJob& J = jobs[f];
+        const uint32_t seg_end = min(hi, cent_prefix[f + 1]);
+        const uint32_t c_begin = g - cent_prefix[f], c_end = seg_end - cent_prefix[f];
+        const uint32_t nwords = (J.l + 31u) >> 5;
+        const uint32_t sw = min((nwords + 3u) & ~3u, smem_words_cap);     // 16 B granules; buffer is padded
+        __syncthreads();                                                    // everyone done with the previous array
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&bar, sw * 4u);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(J.bits);
+            uint8_t* dst = reinterpret_cast<uint8_t*>(sbits);
+            for (uint32_t off = 0; off < sw * 4u; off += 32768u)
+                bulk_g2s(dst + off, src + off, min(32768u, sw * 4u - off), &bar);
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+        const FilterK K = filter_consts(J);
+        BitView bv; bv.sm = sbits; bv.gl = J.bits; bv.sm_words = sw;
+        uint4* pass4 = reinterpret_cast<uint4*>(J.pass);
+        for (uint32_t c = c_begin + threadIdx.x; c < c_end; c += QT) {
+            const Bits128 r = query_century(bv, K, c, min(100u, J.n - 100u * c));
+            pass4[c] = make_uint4((uint32_t)r.lo, (uint32_t)(r.lo >> 32), (uint32_t)r.hi, (uint32_t)(r.hi >> 32));
+        }
+        g = seg_end;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// block-wide exclusive scan helper (1024 threads)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t& block_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < nw ? s_warp[lane] : 0u, wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        s_warp[lane] = wi - w;                          // exclusive warp offsets
+        if (lane == 31) s_warp[32] = wi;                // block total
+    }
+    __syncthreads();
+    const uint32_t res = s_warp[warp] + inc - v;
+    block_total = s_warp[32];
+    __syncthreads();
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3b: witness.  One CTA per frame walks the centuries in order; witness = mask bits at the
+// passing positions (ivc:253), concatenated.  Finishes by converting witness and bit array
+// to np.packbits order in place (ivc:945, ivc:951).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_witness(const FrameJob* __restrict__ jobs, uint32_t* __restrict__ wlen_out) {
+    const FrameJob& J = jobs[blockIdx.x];
+    __shared__ uint32_t s_warp[33];
+    if (J.l == 0) { if (threadIdx.x == 0) wlen_out[blockIdx.x] = 0; return; }
+    const uint32_t ncent = (J.n + 99u) / 100u;
+    const uint4* pass4 = reinterpret_cast<const uint4*>(J.pass);
+    uint32_t base = 0;
+    for (uint32_t r0 = 0; r0 < ncent; r0 += blockDim.x) {
+        const uint32_t c = r0 + threadIdx.x;
+        uint64_t wlo = 0, whi = 0;
+        uint32_t cnt = 0;
+        if (c < ncent) {
+            const uint4 p = pass4[c];
+            const Bits128 mb = load_bits100(J.mask, c, min(100u, J.n - 100u * c));
+            const uint32_t P[4] = {p.x, p.y, p.z, p.w};
+            const uint32_t M[4] = {(uint32_t)mb.lo, (uint32_t)(mb.lo >> 32), (uint32_t)mb.hi, (uint32_t)(mb.hi >> 32)};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t pw = P[j];
+                while (pw) {
+                    const uint32_t b = __ffs(pw) - 1;
+                    pw &= pw - 1u;
+                    const uint64_t bit = (M[j] >> b) & 1u;
+                    if (cnt < 64u) wlo |= bit << cnt; else whi |= bit << (cnt - 64u);
+                    cnt++;
+                }
+            }
+        }
+        uint32_t tot;
+        const uint32_t off = block_excl_scan(cnt, s_warp, tot);
+        if (cnt) or_bits128(J.witness, (uint64_t)base + off, wlo, whi);
+        base += tot;
+    }
+    __syncthreads();
+    __threadfence_block();
+    const uint32_t wwords = (base + 31u) >> 5;
+    for (uint32_t i = threadIdx.x; i < wwords; i += blockDim.x) J.witness[i] = bitrev_bytes(__ldcg(J.witness + i));
+    const uint32_t bwords = (J.l + 31u) >> 5;
+    for (uint32_t i = threadIdx.x; i < bwords; i += blockDim.x) J.bits[i] = bitrev_bytes(__ldcg(J.bits + i));
+    if (threadIdx.x == 0) wlen_out[blockIdx.x] = base;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4b: decode expand.  out[i] = witness[rank of i among passing positions] (ivc:299-304).
+// Witness here is LSB-first (the host converts the packbits input once with k_bitrev).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_expand(const FrameJob* __restrict__ jobs, uint32_t* __restrict__ consumed) {
+    const FrameJob& J = jobs[blockIdx.x];
+    __shared__ uint32_t s_warp[33];
+    if (J.l == 0) { if (threadIdx.x == 0) consumed[blockIdx.x] = 0; return; }
+    const uint32_t ncent = (J.n + 99u) / 100u;
+    const uint4* pass4 = reinterpret_cast<const uint4*>(J.pass);
+    uint32_t base = 0;
+    for (uint32_t r0 = 0; r0 < ncent; r0 += blockDim.x) {
+        const uint32_t c = r0 + threadIdx.x;
+        uint4 p = make_uint4(0, 0, 0, 0);
+        uint32_t cnt = 0;
+        if (c < ncent) { p = pass4[c]; cnt = __popc(p.x) + __popc(p.y) + __popc(p.z) + __popc(p.w); }
+        uint32_t tot;
+        const uint32_t off = base + block_excl_scan(cnt, s_warp, tot);
+        if (cnt) {
+            // fetch cnt (<=100) witness bits starting at bit `off`; bits at or beyond wlen_in read as 0
+            const uint32_t w = off >> 5, sh = off & 31u;
+            const uint32_t lim = (J.wlen_in + 31u) >> 5;
+            uint32_t a[5];
+#pragma unroll
+            for (int j = 0; j < 5; j++) a[j] = (w + j < lim) ? __ldg(J.witness + w + j) : 0u;
+            uint32_t s[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) s[j] = __funnelshift_r(a[j], a[j + 1], sh);
+            uint64_t wl = (uint64_t)s[0] | ((uint64_t)s[1] << 32), wh = (uint64_t)s[2] | ((uint64_t)s[3] << 32);
+            // bits beyond wlen_in are zero by construction of the padded buffer tail (host zero-fills)
+            const uint32_t P[4] = {p.x, p.y, p.z, p.w};
+            uint32_t O[4] = {0, 0, 0, 0};
+            uint32_t k = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t pw = P[j];
+                while (pw) {
+                    const uint32_t b = __ffs(pw) - 1;
+                    pw &= pw - 1u;
+                    const uint32_t bit = (uint32_t)(((k < 64u) ? (wl >> k) : (wh >> (k - 64u))) & 1ull);
+                    const uint32_t valid = (off + k < J.wlen_in) ? 1u : 0u;
+                    O[j] |= (bit & valid) << b;
+                    k++;
+                }
+            }
+            or_bits128(J.out_mask, 100ull * c, (uint64_t)O[0] | ((uint64_t)O[1] << 32), (uint64_t)O[2] | ((uint64_t)O[3] << 32));
+        }
+        base += tot;
+    }
+    if (threadIdx.x == 0) consumed[blockIdx.x] = base;
+}
+
+// ------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------
+__global__ void k_bitrev(uint32_t* __restrict__ w, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        w[i] = bitrev_bytes(w[i]);
+}
+// LSB-first packed bits -> one byte per bit (np.uint8 0/1)
+__global__ void k_unpack_bits(const uint32_t* __restrict__ w, uint8_t* __restrict__ out, size_t nbits) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nbits; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (uint8_t)((w[i >> 5] >> (i & 31)) & 1u);
+}
+// one byte per position (== 1 is set, as `binary_input[i] == 1`, ivc:236) -> LSB-first packed words
+__global__ void k_pack_bytes(const uint8_t* __restrict__ in, uint32_t* __restrict__ w, size_t nbits) {
+    const size_t nwords = (nbits + 31) >> 5;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t v = 0;
+        const size_t b0 = i << 5;
+        for (uint32_t k = 0; k < 32u && b0 + k < nbits; k++) v |= (in[b0 + k] == 1 ? 1u : 0u) << k;
+        w[i] = v;
+    }
+}
+
+
+// MSB-first (np.packbits order) packed bits -> one byte per bit
+__global__ void k_unpack_bits_msb(const uint32_t* __restrict__ w, uint8_t* __restrict__ out, size_t nbits) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nbits; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (uint8_t)((w[i >> 5] >> ((i & 31) ^ 7)) & 1u);
+}
+__global__ void k_popcount(const uint32_t* __restrict__ w, size_t n, uint32_t* __restrict__ out) {
+    uint32_t c = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) c += __popc(w[i]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+// per frame: number of 32-bit words in which two packed bit arrays differ
+__global__ void k_count_diff(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, size_t stride_words,
+                             size_t nwords, uint32_t* __restrict__ out) {
+    const uint32_t* pa = a + (size_t)blockIdx.y * stride_words;
+    const uint32_t* pb = b + (size_t)blockIdx.y * stride_words;
+    uint32_t c = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x)
+        c += (pa[i] != pb[i]) ? 1u : 0u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out + blockIdx.y, c);
+}
+
+// ------------------------------------------------------------------------------------------
+// explicit-item kernels: RationalBloomFilter.add_index / check_index on a list of indices
+// (ivc:99-138), and the string-keyed twin rbf.RationalBloomFilter / StandardBloomFilter
+// (rbf:25-41, rbf:103-182).  Bit array is LSB-first in global memory.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t check_hashes_global(const uint32_t* __restrict__ bits, const FilterK& K, uint64_t h1,
+                                                        uint64_t h2, uint64_t hA) {
+    uint32_t idx = mod_u64(h1, K.fm);
+    const uint32_t step = mod_u64(h2, K.fm);
+    for (uint32_t i = 0; i < K.fk; i++) {
+        if (!((bits[idx >> 5] >> (idx & 31u)) & 1u)) return 0u;
+        idx = addmod(idx, step, K.fm.m);
+    }
+    if (K.has_act && hA < K.T) { if (!((bits[idx >> 5] >> (idx & 31u)) & 1u)) return 0u; }
+    return 1u;
+}
+
+__global__ void k_items_u32(const FrameJob* __restrict__ job, const uint32_t* __restrict__ items, uint32_t count,
+                            uint8_t* __restrict__ result, int insert) {
+    const FrameJob& J = *job;
+    const FilterK K = filter_consts(J);
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+        const uint32_t i = items[t];
+        const Century cen = make_century(i / 100u);
+        const uint32_t x = (i / 10u) % 10u, y = i % 10u;
+        const uint64_t h1 = finish(cen.kind, decade_state(cen, century_state(cen, K.s1), K.s1, x), K.s1, y);
+        const uint64_t h2 = finish(cen.kind, decade_state(cen, century_state(cen, K.s2), K.s2, x), K.s2, y);
+        const uint64_t hA = K.has_act ? finish(cen.kind, decade_state(cen, century_state(cen, K.sA), K.sA, x), K.sA, y) : 0ull;
+        if (insert) insert_hashes(J.bits, K, h1, h2, hA);
+        else result[t] = (uint8_t)check_hashes_global(J.bits, K, h1, h2, hA);
+    }
+}
+
+__global__ void k_items_str(const FrameJob* __restrict__ job, const uint8_t* __restrict__ blob,
+                            const uint64_t* __restrict__ offs, uint32_t count, uint8_t* __restrict__ result, int insert,
+                            int standard_k) {
+    const FrameJob& J = *job;
+    const FilterK K = filter_consts(J);
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+        const uint8_t* s = blob + offs[t];
+        const uint32_t len = (uint32_t)(offs[t + 1] - offs[t]);
+        if (standard_k > 0) {           // StandardBloomFilter: k independent hashes, seed = i (rbf:25-41)
+            uint32_t ok = 1u;
+            for (int i = 0; i < standard_k; i++) {
+                const uint32_t idx = mod_u64(xxh64_bytes(s, len, (uint64_t)i), K.fm);
+                if (insert) atomicOr(J.bits + (idx >> 5), 1u << (idx & 31u));
+                else if (!((J.bits[idx >> 5] >> (idx & 31u)) & 1u)) { ok = 0u; break; }
+            }
+            if (!insert) result[t] = (uint8_t)ok;
+        } else {
+            const uint64_t h1 = xxh64_bytes(s, len, K.s1), h2 = xxh64_bytes(s, len, K.s2);
+            const uint64_t hA = K.has_act ? xxh64_bytes(s, len, K.sA) : 0ull;
+            if (insert) insert_hashes(J.bits, K, h1, h2, hA);
+            else result[t] = (uint8_t)check_hashes_global(J.bits, K, h1, h2, hA);
+        }
+    }
+}
+
+// KAT / debug: mode 0 = xxh64_decimal(item), mode 1 = century/decade/finish route
+__global__ void k_hash_debug(const uint32_t* __restrict__ items, uint32_t count, uint64_t seed, uint64_t* __restrict__ out,
+                             int mode) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+        const uint32_t i = items[t];
+        if (mode == 0) out[t] = xxh64_decimal(i, seed);
+        else {
+            const Century cen = make_century(i / 100u);
+            out[t] = finish(cen.kind, decade_state(cen, century_state(cen, seed), seed, (i / 10u) % 10u), seed, i % 10u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+template <int PB, int S>
+static cudaError_t launch_threshold_t(const PairJob* d_pairs, int F, uint32_t npix, int thr, int any_mode, uint32_t* d_ones,
+                                      uint32_t* d_resid, int variant, int sm_count, cudaStream_t st) {
+    const uint32_t nwords = (npix + 31u) >> 5;
+    constexpr uint32_t TP = TMA_TILE_BYTES / PB;
+    if (variant == 1 && npix >= TP && (TP / 32u / (TMA_THREADS / 32)) <= 32u) {
+        const int smem = 2 * TMA_STAGES * TMA_TILE_BYTES;
+        cudaError_t e = cudaFuncSetAttribute(k_threshold_tma<PB, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        const uint64_t total = (uint64_t)(npix / TP) * (uint64_t)F;
+        int grid = (int)((total < (uint64_t)(2 * sm_count)) ? total : (uint64_t)(2 * sm_count));
+        k_threshold_tma<PB, S><<<grid, TMA_THREADS, smem, st>>>(d_pairs, F, npix, thr, any_mode, d_ones, d_resid);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        const uint32_t px_begin = (npix / TP) * TP;
+        if (px_begin < npix) {
+            const uint32_t tail_words = nwords - (px_begin >> 5);
+            dim3 g((tail_words + 255u) / 256u, (unsigned)F);
+            k_threshold_tail<PB, S><<<g, 256, 0, st>>>(d_pairs, npix, px_begin, thr, any_mode, d_ones, d_resid);
+        }
+        return cudaGetLastError();
+    }
+    uint32_t bx = (nwords + 255u) / 256u;
+    const uint32_t cap = (uint32_t)(sm_count * 32);
+    if ((uint64_t)bx * (uint64_t)F > cap) { bx = (cap + (uint32_t)F - 1u) / (uint32_t)F; if (bx < 1u) bx = 1u; }
+    dim3 grid(bx, (unsigned)F);
+    k_threshold<PB, S><<<grid, 256, 0, st>>>(d_pairs, npix, thr, any_mode, d_ones, d_resid);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_threshold(const PairJob* d_pairs, int F, uint32_t npix, int channels, int sample_bytes, int thr_int,
+                             int any_mode, uint32_t* d_ones, uint32_t* d_resid, int variant, int sm_count, cudaStream_t st) {
+    if (F <= 0 || npix == 0) return cudaSuccess;
+    const int pb = channels * sample_bytes;
+    if (pb == 3 && sample_bytes == 1) return launch_threshold_t<3, 1>(d_pairs, F, npix, thr_int, any_mode, d_ones, d_resid, variant, sm_count, st);
+    if (pb == 6 && sample_bytes == 2) return launch_threshold_t<6, 2>(d_pairs, F, npix, thr_int, any_mode, d_ones, d_resid, variant, sm_count, st);
+    if (pb == 1 && sample_bytes == 1) return launch_threshold_t<1, 1>(d_pairs, F, npix, thr_int, any_mode, d_ones, d_resid, variant, sm_count, st);
+    if (pb == 2 && sample_bytes == 2) return launch_threshold_t<2, 2>(d_pairs, F, npix, thr_int, any_mode, d_ones, d_resid, variant, sm_count, st);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_insert(const FrameJob* d_jobs, int F, uint32_t max_centuries, int sm_count, cudaStream_t st) {
+    if (F <= 0 || max_centuries == 0) return cudaSuccess;
+    uint32_t bx = (max_centuries + 255u) / 256u;
+    const uint32_t cap = (uint32_t)(sm_count * 16);
+    if ((uint64_t)bx * (uint64_t)F > cap) { bx = (cap + (uint32_t)F - 1u) / (uint32_t)F; if (bx < 1u) bx = 1u; }
+    dim3 grid(bx, (unsigned)F);
+    k_insert<<<grid, 256, 0, st>>>(d_jobs);
+    return cudaGetLastError();
+}
+
+int query_max_smem_bytes() { return 232448 - 1024; }    // 227 KB opt-in minus static shared memory + slack
+
+cudaError_t launch_query(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, int F, uint32_t total_centuries,
+                         int sm_count, int smem_bytes_cap, cudaStream_t st) {
+    if (F <= 0 || total_centuries == 0) return cudaSuccess;
+    int smem = smem_bytes_cap & ~15;
+    if (smem > query_max_smem_bytes()) smem = query_max_smem_bytes() & ~15;
+    if (smem < 16) smem = 16;
+    cudaError_t e = cudaFuncSetAttribute(k_query, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_query, QT, (size_t)smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = (uint32_t)(sm_count * per_sm);
+    const uint32_t max_useful = (total_centuries + QT - 1) / QT;
+    if (grid > max_useful) grid = max_useful;
+    if (grid < 1u) grid = 1u;
+    k_query<<<grid, QT, smem, st>>>(d_jobs, d_cent_prefix, F, (uint32_t)(smem / 4));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_witness(const FrameJob* d_jobs, int F, uint32_t* d_wlen, cudaStream_t st) {
+    if (F <= 0) return cudaSuccess;
+    k_witness<<<F, 1024, 0, st>>>(d_jobs, d_wlen);
+    return cudaGetLastError();
+}
+cudaError_t launch_expand(const FrameJob* d_jobs, int F, uint32_t* d_consumed, cudaStream_t st) {
+    if (F <= 0) return cudaSuccess;
+    k_expand<<<F, 1024, 0, st>>>(d_jobs, d_consumed);
+    return cudaGetLastError();
+}
+static inline unsigned grid_for(size_t n, unsigned block) {
+    size_t g = (n + block - 1) / block;
+    if (g > 148u * 16u) g = 148u * 16u;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+cudaError_t launch_bitrev(uint32_t* d_words, size_t nwords, cudaStream_t st) {
+    if (nwords == 0) return cudaSuccess;
+    k_bitrev<<<grid_for(nwords, 256), 256, 0, st>>>(d_words, nwords);
+    return cudaGetLastError();
+}
+cudaError_t launch_unpack_bits(const uint32_t* d_words, uint8_t* d_out, size_t nbits, cudaStream_t st) {
+    if (nbits == 0) return cudaSuccess;
+    k_unpack_bits<<<grid_for(nbits, 256), 256, 0, st>>>(d_words, d_out, nbits);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack_bytes(const uint8_t* d_bytes, uint32_t* d_words, size_t nbits, cudaStream_t st) {
+    if (nbits == 0) return cudaSuccess;
+    k_pack_bytes<<<grid_for((nbits + 31) / 32, 256), 256, 0, st>>>(d_bytes, d_words, nbits);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_bits_msb(const uint32_t* d_words, uint8_t* d_out, size_t nbits, cudaStream_t st) {
+    if (nbits == 0) return cudaSuccess;
+    k_unpack_bits_msb<<<grid_for(nbits, 256), 256, 0, st>>>(d_words, d_out, nbits);
+    return cudaGetLastError();
+}
+cudaError_t launch_popcount(const uint32_t* d_words, size_t nwords, uint32_t* d_out, cudaStream_t st) {
+    if (nwords == 0) return cudaSuccess;
+    k_popcount<<<grid_for(nwords, 256), 256, 0, st>>>(d_words, nwords, d_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_count_diff(const uint32_t* a, const uint32_t* b, size_t stride_words, size_t nwords, int F,
+                              uint32_t* d_out, cudaStream_t st) {
+    if (nwords == 0 || F <= 0) return cudaSuccess;
+    unsigned gx = grid_for(nwords, 256);
+    if (gx > 64u) gx = 64u;
+    dim3 g(gx, (unsigned)F);
+    k_count_diff<<<g, 256, 0, st>>>(a, b, stride_words, nwords, d_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_items_u32(const FrameJob* d_job, const uint32_t* d_items, uint32_t count, uint8_t* d_result, int insert,
+                             cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    k_items_u32<<<grid_for(count, 256), 256, 0, st>>>(d_job, d_items, count, d_result, insert);
+    return cudaGetLastError();
+}
+cudaError_t launch_items_str(const FrameJob* d_job, const uint8_t* d_blob, const uint64_t* d_offs, uint32_t count,
+                             uint8_t* d_result, int insert, int standard_k, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    k_items_str<<<grid_for(count, 128), 128, 0, st>>>(d_job, d_blob, d_offs, count, d_result, insert, standard_k);
+    return cudaGetLastError();
+}
+cudaError_t launch_hash_debug(const uint32_t* d_items, uint32_t count, uint64_t seed, uint64_t* d_out, int mode,
+                              cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    k_hash_debug<<<grid_for(count, 256), 256, 0, st>>>(d_items, count, seed, d_out, mode);
+    return cudaGetLastError();
+}
+
+}  // namespace rbf

@@ -1,0 +1,125 @@
+"""
+FrameStream: Python handle on the C ABI's rbf_stream -- a device-resident store of
+interleaved H x W x C frames plus the per-pair outputs of the batched hot path
+(K1 threshold -> exact (k, l, T) on the host -> K2 insert -> K3 query -> K3b witness).
+No PyTorch; device memory belongs to the C library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import MaskInfo
+
+
+class PairResult:
+    """What BloomFilterCompressor.compress returns for one frame pair (ivc:266), in wire form."""
+    __slots__ = ("n", "ones", "resid", "l", "wlen", "p", "k", "raw", "floor_k", "act_T")
+
+    def __init__(self, mi: MaskInfo):
+        self.n, self.ones, self.resid, self.l, self.wlen = int(mi.n), int(mi.ones), int(mi.resid), int(mi.l), int(mi.wlen)
+        self.p, self.k, self.raw, self.floor_k, self.act_T = float(mi.p), float(mi.k), bool(mi.raw), int(mi.floor_k), int(mi.act_T)
+
+    def __repr__(self):
+        return "PairResult(n=%d ones=%d l=%d wlen=%d k=%r raw=%s)" % (self.n, self.ones, self.l, self.wlen, self.k, self.raw)
+
+
+class FrameStream:
+    def __init__(self, height: int, width: int, channels: int = 3, dtype=np.uint8, max_frames: int = 2,
+                 max_pairs: Optional[int] = None):
+        dt = np.dtype(dtype)
+        if dt not in (np.dtype(np.uint8), np.dtype(np.uint16)):
+            raise ValueError("frames must be uint8 or uint16")
+        self.H, self.W, self.C, self.dtype = int(height), int(width), int(channels), dt
+        self.max_frames = int(max_frames)
+        self.max_pairs = int(max_pairs if max_pairs is not None else max(1, max_frames - 1))
+        self.npix = self.H * self.W
+        self._h = C.c_void_p()
+        _cabi.check(_cabi.lib().rbf_stream_create(_cabi.ctx(), self.H, self.W, self.C, dt.itemsize, self.max_frames,
+                                                  self.max_pairs, C.byref(self._h)), _cabi.ctx())
+        self._infos = (MaskInfo * self.max_pairs)()
+        self.pairs = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _cabi.lib().rbf_stream_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ data movement
+    def upload(self, frames: np.ndarray, first: int = 0) -> None:
+        """frames: [count, H, W, C] (or [H, W, C]) contiguous array of the stream's dtype."""
+        a = np.ascontiguousarray(frames)
+        if a.ndim == 3 and self.C > 1 or (a.ndim == 2 and self.C == 1):
+            a = a[None]
+        if a.dtype != self.dtype or a.shape[1:3] != (self.H, self.W):
+            raise ValueError("frame shape/dtype mismatch: %r %r" % (a.shape, a.dtype))
+        _cabi.check(_cabi.lib().rbf_stream_upload(self._h, int(first), int(a.shape[0]), _cabi.ptr(a)), _cabi.ctx())
+
+    # ------------------------------------------------------------------ the hot path
+    def encode(self, prev_idx: Sequence[int], curr_idx: Sequence[int], threshold: float,
+               seeds=_cabi.IVC_SEEDS, k_override=None, l_override=None) -> List[PairResult]:
+        p = np.ascontiguousarray(np.asarray(prev_idx, dtype=np.uint32))
+        c = np.ascontiguousarray(np.asarray(curr_idx, dtype=np.uint32))
+        if p.shape != c.shape or p.ndim != 1:
+            raise ValueError("prev_idx and curr_idx must be 1-D and equally long")
+        sd = _cabi.seeds_struct(seeds)
+        ko = lo = None
+        if k_override is not None:
+            ko = np.ascontiguousarray(np.asarray(k_override, dtype=np.float64))
+            lo = np.ascontiguousarray(np.asarray(l_override, dtype=np.uint64))
+        _cabi.check(_cabi.lib().rbf_stream_encode(self._h, _cabi.ptr(p), _cabi.ptr(c), p.size, float(threshold), C.byref(sd),
+                                                  _cabi.ptr(ko) if ko is not None else None,
+                                                  _cabi.ptr(lo) if lo is not None else None, self._infos), _cabi.ctx())
+        self.pairs = int(p.size)
+        return [PairResult(self._infos[i]) for i in range(self.pairs)]
+
+    def encode_consecutive(self, nframes: int, threshold: float, **kw) -> List[PairResult]:
+        idx = np.arange(nframes, dtype=np.uint32)
+        return self.encode(idx[:-1], idx[1:], threshold, **kw)
+
+    def fetch(self, pair: int, want_mask: bool = True):
+        """-> (bitmap_packbits uint8[ceil(l/8)], witness_packbits uint8[ceil(wlen/8)], mask uint8[n] or None)."""
+        mi = self._infos[pair]
+        bm = np.zeros((int(mi.l) + 7) // 8, dtype=np.uint8)
+        wt = np.zeros((int(mi.wlen) + 7) // 8, dtype=np.uint8)
+        mk = np.zeros((self.npix + 7) // 8, dtype=np.uint8) if want_mask else None
+        _cabi.check(_cabi.lib().rbf_stream_fetch(self._h, int(pair), _cabi.ptr(bm) if bm.size else None,
+                                                 _cabi.ptr(wt) if wt.size else None,
+                                                 _cabi.ptr(mk) if mk is not None else None), _cabi.ctx())
+        mask = np.unpackbits(mk, bitorder="little")[: self.npix] if mk is not None else None
+        return bm, wt, mask
+
+    def decode_verify(self, pairs: Optional[int] = None) -> np.ndarray:
+        """Decode every encoded pair on the GPU from its own bitmap + witness (ivc:268-307) and
+        return the number of mismatching mask words per pair (all zeros == round trip holds)."""
+        n = self.pairs if pairs is None else int(pairs)
+        out = np.zeros(n, dtype=np.uint64)
+        _cabi.check(_cabi.lib().rbf_stream_decode_verify(self._h, n, _cabi.ptr(out)), _cabi.ctx())
+        return out
+
+    def stage_ms(self) -> dict:
+        out = (C.c_double * 5)()
+        _cabi.check(_cabi.lib().rbf_stream_stage_ms(self._h, out), _cabi.ctx())
+        return dict(zip(("k1_threshold", "host_params", "k2_insert", "k3_query", "k3b_witness"), [float(x) for x in out]))
+
+    def encode_host(self, frames: np.ndarray, threshold: float, seeds=_cabi.IVC_SEEDS, bitmap_slot: int = 0,
+                    witness_slot: int = 0, out_bitmaps: np.ndarray = None, out_witness: np.ndarray = None):
+        """End-to-end call: host frames in, packed bitmaps/witnesses back in host slots (copies included)."""
+        a = np.ascontiguousarray(frames)
+        nfr = a.shape[0]
+        sd = _cabi.seeds_struct(seeds)
+        _cabi.check(_cabi.lib().rbf_stream_encode_host(
+            self._h, _cabi.ptr(a), nfr, float(threshold), C.byref(sd), self._infos,
+            _cabi.ptr(out_bitmaps) if out_bitmaps is not None else None, int(bitmap_slot),
+            _cabi.ptr(out_witness) if out_witness is not None else None, int(witness_slot)), _cabi.ctx())
+        self.pairs = nfr - 1
+        return [PairResult(self._infos[i]) for i in range(self.pairs)]

@@ -315,6 +315,24 @@ def gen_strings():
     dump("strings_kat.json", {"items_seed": 42, "filters": recs, "optimal_size": opt, "optimal_hash_count": hc})
 
 
+# ---------------------------------------------------------------- keyframe payloads (host glue, fvc:27-74)
+def gen_keyframes():
+    comp = fvc.FixedVideoCompressor(verbose=False)
+    arrays, recs = {}, []
+    for name, shape, dt, yuv in [("bgr_u8", (24, 40, 3), np.uint8, False), ("yuv_u8", (24, 40, 3), np.uint8, True),
+                                 ("gray_u8", (16, 16), np.uint8, False), ("yuv_u16", (8, 12, 3), np.uint16, False)]:
+        rng = np.random.default_rng(77)
+        hi = 256 if dt == np.uint8 else 65536
+        f = (rng.integers(0, hi, shape) // 16 * 16).astype(dt)
+        fr = comp.add_yuv_info_to_frame(f) if yuv else f
+        payload = comp.compress_frame(fr)
+        arrays[name + "/frame"] = f
+        arrays[name + "/payload"] = np.frombuffer(payload, dtype=np.uint8)
+        recs.append({"name": name, "yuv": yuv, "payload_sha256": hashlib.sha256(payload).hexdigest()})
+    dump("keyframe_kat.json", {"cases": recs})
+    np.savez_compressed(os.path.join(HERE, "keyframe_arrays.npz"), **arrays)
+
+
 if __name__ == "__main__":
     gen_xxh64()
     gen_filter()
@@ -323,3 +341,4 @@ if __name__ == "__main__":
     gen_compress()
     gen_frames()
     gen_strings()
+    gen_keyframes()

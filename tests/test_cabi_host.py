@@ -1,0 +1,109 @@
+"""CPU tests (-m "not gpu") of the product's C-ABI library: it loads, exports every symbol
+include/rbf_b200.h declares, its exact host-side scalars match the golden vectors, and it
+refuses to compute without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests.util import golden_json
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def cabi():
+    from new_bloom_filter_repo_b200 import build, _cabi
+    build.build()
+    return _cabi
+
+
+def test_header_symbols_exported(cabi):
+    hdr = open(os.path.join(ROOT, "include", "rbf_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(rbf_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 45
+    L = C.CDLL(cabi.SO_PATH)
+    missing = [n for n in declared if not hasattr(L, n)]
+    assert not missing, missing
+    assert sorted(cabi.EXPORTS) == declared
+    assert cabi.lib().rbf_abi_version() == 1
+
+
+def test_host_xxh64_matches_golden(cabi):
+    g = golden_json("xxh64_kat.json")
+    L = cabi.lib()
+    for rec in g["decimal"]:
+        for s, d in zip(g["seeds"], rec["digests"]):
+            assert format(L.rbf_hash_decimal(rec["item"], s), "016x") == d
+            assert format(L.rbf_hash_decimal_century(rec["item"], s), "016x") == d      # the route the kernels take
+    for rec in g["strings"]:
+        b = rec["s"].encode("utf-8")
+        for s, d in zip(g["seeds"], rec["digests"]):
+            assert format(cabi.xxh64(b, s), "016x") == d
+
+
+def test_century_route_dense_ranges(cabi):
+    L = cabi.lib()
+    rng = np.random.default_rng(3)
+    items = np.concatenate([np.arange(0, 12000), np.arange(99000, 101200), np.arange(999900, 1000200),
+                            np.arange(9999900, 10000200), np.arange(99999900, 100000200),
+                            np.arange(999999900, 1000000200), np.arange(2 ** 32 - 300, 2 ** 32),
+                            rng.integers(0, 2 ** 32, 20000)])
+    for seed in (0x12345678, 0x87654321, 999):
+        for it in items[::3]:
+            it = int(it)
+            assert L.rbf_hash_decimal(it, seed) == L.rbf_hash_decimal_century(it, seed), it
+
+
+def test_probe_index_and_threshold(cabi):
+    g = golden_json("filter_kat.json")
+    L = cabi.lib()
+    for rec in g["filters"]:
+        T = cabi.activation_threshold(float.fromhex(rec["p_activation"]))
+        for it, probes, act in zip(rec["items"], rec["probes"], rec["activation"]):
+            b = str(it).encode()
+            h1, h2 = cabi.xxh64(b, 0x12345678), cabi.xxh64(b, 0x87654321)
+            assert [L.rbf_probe_index(h1, h2, i, rec["size"]) for i in range(rec["floor_k"] + 1)] == probes
+            assert (cabi.xxh64(b, 999) < T) == act
+    a = golden_json("activation_kat.json")
+    for rec in a["thresholds"]:
+        T = int(rec["T"], 16)
+        if T < 2 ** 64:
+            assert cabi.activation_threshold(float.fromhex(rec["p"])) == T
+
+
+def test_optimal_params_matches_reference(cabi):
+    g = golden_json("params_kat.json")
+    for rec in g["cases"]:
+        coded, p, k, l = cabi.optimal_params(rec["n"], rec["ones"])
+        assert float(p).hex() == rec["p"]
+        kr, lr = float.fromhex(rec["k"]), rec["l"]
+        ref_coded = not (float.fromhex(rec["p"]) >= 0.32453) and not (lr == 0 or lr >= rec["n"])
+        assert coded == ref_coded, rec
+        if coded:
+            assert (float(k).hex(), l) == (float(kr).hex(), lr), rec
+
+
+def test_no_cpu_fallback(cabi):
+    """Without a GPU the product must raise, not compute (run only where no GPU is visible)."""
+    h = C.c_void_p()
+    rc = cabi.lib().rbf_ctx_create(0, C.byref(h))
+    if rc == 0:
+        cabi.lib().rbf_ctx_destroy(h)
+        pytest.skip("a GPU is present")
+    assert rc == -3
+    assert b"no CPU fallback" in cabi.lib().rbf_last_global_error()
+    import new_bloom_filter_repo_b200 as pkg
+    with pytest.raises(pkg.RbfError):
+        pkg.BloomFilterCompressor().compress(np.zeros(100, dtype=np.uint8))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "new_bloom_filter_repo_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f

@@ -1,0 +1,356 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI / the drop-in classes,
+against (i) the golden fixtures generated from the real reference and (ii) the oracle on the
+same seeded inputs.  Integer / bit work: every comparison is bit-exact."""
+import math
+import random
+
+import numpy as np
+import pytest
+
+from tests.util import golden_json, golden_npz, golden_pair, mask_for, sha, synth_pair, synth_stream
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import new_bloom_filter_repo_b200 as p
+    info = p._cabi.device_info()
+    assert info["cc"][0] >= 10, info
+    return p
+
+
+@pytest.fixture(scope="module")
+def co():
+    from oracle import c_oracle
+    c_oracle.build()
+    return c_oracle
+
+
+# ------------------------------------------------------------------ filter (ivc:39-138)
+def test_index_filter_against_golden(pkg):
+    g = golden_json("filter_kat.json")
+    for rec in g["filters"]:
+        f = pkg.IndexRationalBloomFilter(rec["size"], rec["k"])
+        assert f.floor_k == rec["floor_k"] and float(f.p_activation).hex() == rec["p_activation"]
+        if rec["size"] > 5_000_000:          # bit_array of 2^31 bytes is not worth materialising
+            for it, probes in zip(rec["items"][:4], rec["probes"][:4]):
+                assert [f._get_hash_indices(it, i) for i in range(f.floor_k + 1)] == probes
+            continue
+        for it, probes, act in zip(rec["items"], rec["probes"], rec["activation"]):
+            ff = pkg.IndexRationalBloomFilter(rec["size"], rec["k"])
+            ff.add_index(it)
+            expect = set(probes[:rec["floor_k"]]) | ({probes[rec["floor_k"]]} if act else set())
+            got = set(np.nonzero(ff.bit_array)[0].tolist())
+            assert got == expect, (rec["size"], rec["k"], it)
+            assert ff.check_index(it)
+            assert [ff._get_hash_indices(it, i) for i in range(ff.floor_k + 1)] == probes
+            assert ff._determine_activation(it) == act
+
+
+def test_index_filter_survey_kat(pkg):
+    """mask inserted into RationalBloomFilter(1000, 2.3), all 4096 queried."""
+    g = golden_json("compress_kat.json")
+    e = g["explicit_k2.3"]
+    m = mask_for(g["cases"][0])
+    f = pkg.IndexRationalBloomFilter(1000, 2.3)
+    f.add_indices(np.nonzero(m)[0])
+    bits = f.bit_array
+    assert int(bits.sum()) == e["bits_set"] == 382
+    assert sha(np.packbits(bits)) == e["bitmap_sha256"]
+    passed = f.check_indices(np.arange(4096))
+    wit = m[passed]
+    assert len(wit) == e["witness_len"] == 700 and sha(np.packbits(wit)) == e["witness_sha256"]
+    # bit_array assignment (ivc:290)
+    f2 = pkg.IndexRationalBloomFilter(1000, 2.3)
+    f2.bit_array = bits
+    assert np.array_equal(f2.check_indices(np.arange(4096)), passed)
+
+
+# ------------------------------------------------------------------ BloomFilterCompressor (ivc:140-307)
+def test_compress_against_golden(pkg):
+    g = golden_json("compress_kat.json")
+    arrays = golden_npz("compress_arrays.npz")
+    comp = pkg.BloomFilterCompressor()
+    for rec in g["cases"]:
+        m = mask_for(rec)
+        bitmap, witness, p, n, ratio = comp.compress(m)
+        assert float(p).hex() == rec["p"] and n == rec["n"]
+        if rec["raw"]:
+            assert witness == [] and bitmap is m and ratio == 1.0
+            continue
+        w = np.array(witness, dtype=np.uint8)
+        assert len(bitmap) == rec["bitmap_len"] and len(w) == rec["witness_len"], rec["name"]
+        assert sha(np.packbits(bitmap)) == rec["bitmap_sha256"], rec["name"]
+        assert sha(np.packbits(w)) == rec["witness_sha256"], rec["name"]
+        assert float(ratio).hex() == rec["ratio"]
+        assert float(comp.last_info.k).hex() == rec["k"]
+        if rec["name"] + "/bitmap" in arrays:
+            assert np.array_equal(np.packbits(bitmap), arrays[rec["name"] + "/bitmap"])
+        k, l = comp._calculate_optimal_params(n, p)
+        assert (float(k).hex(), l) == (rec["k"], rec["l"])
+        dec = comp.decompress(bitmap, witness, n, k)
+        assert np.array_equal(dec, m)
+        # the reference's own decode uses k rounded to float32 (ivc:938/986): replicate, do not fix
+        k32 = float.fromhex(rec["k_f32"])
+        dec32 = comp.decompress(bitmap, witness + [0] * 64, n, k32)
+        assert sha(np.packbits(dec32)) == rec["decoded_f32k_sha256"], rec["name"]
+
+
+def test_compress_k_sweep_and_seed_variants(pkg, co):
+    g = golden_json("compress_kat.json")
+    sw = g["k_sweep"]
+    m2 = mask_for(sw)
+    p2 = np.sum(m2) / len(m2)
+    comp = pkg.BloomFilterCompressor()
+    for c in sw["cases"]:
+        bitmap, witness, p, n, ratio = comp.compress(m2, k_l_override=(c["k"], c["l"]))
+        assert sha(np.packbits(bitmap)) == c["bitmap_sha256"], c
+        assert len(witness) == c["witness_len"]
+        assert sha(np.packbits(np.array(witness, dtype=np.uint8))) == c["witness_sha256"]
+    s = golden_json("strings_kat.json")
+    rec = [r for r in s["filters"] if r["kind"] == "bc_compress"][0]
+    m = mask_for(rec)
+    bitmap, witness, *_ = pkg.BloomFilterCompressor(seeds=pkg._cabi.BC_SEEDS).compress(m)
+    assert len(bitmap) == rec["l"] and sha(np.packbits(bitmap)) == rec["bitmap_sha256"]
+    assert sha(np.packbits(np.array(witness, dtype=np.uint8))) == rec["witness_sha256"]
+
+
+@pytest.mark.parametrize("n,p_gen,seed", [(1, 0.5, 1), (33, 0.2, 2), (99, 0.1, 3), (100, 0.1, 4), (101, 0.1, 5), (3199, 0.05, 6),
+                                          (3200, 0.05, 7), (3201, 0.05, 8), (65536, 0.003, 9), (99999, 0.12, 10),
+                                          (100001, 0.2, 11), (1000003, 0.05, 12), (2073600, 0.0499, 13), (10 ** 7 + 7, 0.01, 14)])
+def test_compress_vs_oracle_ragged_sizes(pkg, co, n, p_gen, seed):
+    m = mask_for({"n": n, "p_gen": p_gen, "seed": seed})
+    ob, ow, op, on, oratio, ok, ol = co.compress(m)
+    bitmap, witness, p, nn, ratio = pkg.BloomFilterCompressor().compress(m)
+    assert float(p) == op and nn == on
+    if ok == 0:
+        assert witness == [] and np.array_equal(bitmap, m)
+        return
+    assert len(bitmap) == ol and np.array_equal(bitmap, ob)
+    assert np.array_equal(np.array(witness, dtype=np.uint8), ow)
+    assert ratio == oratio
+    dec = pkg.BloomFilterCompressor().decompress(bitmap, witness, n, ok)
+    assert np.array_equal(dec, m)
+
+
+def test_decompress_short_witness_raises(pkg):
+    m = mask_for({"n": 5000, "p_gen": 0.05, "seed": 3})
+    comp = pkg.BloomFilterCompressor()
+    bitmap, witness, p, n, _ = comp.compress(m)
+    k, l = comp._calculate_optimal_params(n, p)
+    with pytest.raises(IndexError):
+        comp.decompress(bitmap, witness[:-5], n, k)
+    assert comp.decompress(bitmap, [], n, k) is bitmap       # ivc:282-284
+
+
+# ------------------------------------------------------------------ frame diff (ivc:768-847) + payload (ivc:911-1027)
+def test_frame_diff_against_golden(pkg, co):
+    g = golden_json("frames_kat.json")
+    arrays = golden_npz("frames_arrays.npz")
+    vfc = pkg.VideoFrameCompressor(use_direct_yuv=True)
+    for rec in g["cases"]:
+        prev, curr = golden_pair(rec)
+        pf, cf = pkg.YUVFrame(prev), pkg.YUVFrame(curr)
+        mask, changed, dens = vfc._calculate_frame_diff(pf, cf, threshold=rec["threshold"])
+        assert mask.shape == (rec["h"], rec["w"]) and mask.dtype == np.uint8
+        assert int(mask.sum()) == rec["ones"], rec["name"]
+        assert sha(np.packbits(mask.reshape(-1))) == rec["mask_sha256"], rec["name"]
+        assert float(dens).hex() == rec["density"]
+        assert len(changed) == rec["changed_len"] and sha(changed) == rec["changed_sha256"]
+        if "wrap_mask_head" in rec:
+            assert [int(x) for x in mask[0, :5]] == rec["wrap_mask_head"]
+        if "payload_len" in rec:
+            payload, ratio = vfc._compress_frame_differences(mask, changed)
+            assert payload == arrays[rec["name"] + "/payload"].tobytes(), rec["name"]
+            dmask, dchanged = vfc._decompress_frame_differences(payload, curr.shape)
+            assert np.array_equal(dmask, mask) == rec["decoded_mask_equal"]
+            recon = vfc._apply_frame_diff(pf, dmask, dchanged)
+            assert sha(recon.data) == rec["recon_sha256"]
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("shape,dtype,thr", [((64, 64), np.uint8, 3.0), ((37, 53), np.uint8, 0.0), ((1080, 1920), np.uint8, 3.0),
+                                             ((130, 4099), np.uint8, 10.5), ((270, 480), np.uint16, 3.0), ((33, 65), np.uint16, 20000.0),
+                                             ((2160, 3840), np.uint8, 3.0)])
+def test_threshold_kernel_variants_vs_oracle(pkg, co, variant, shape, dtype, thr):
+    """K1 with vectorised loads (0) and with the TMA bulk-copy ring (1): same mask, same counts."""
+    L, ctx = pkg._cabi.lib(), pkg._cabi.ctx()
+    prev, curr = synth_pair(shape[0], shape[1], 99, 0.05, dtype)
+    curr[0, 0, 1] ^= 1          # chroma-only change: not in the Y mask, counted as residual
+    omask, oones = co.frame_diff_mask(prev, curr, thr)
+    st = pkg.FrameStream(shape[0], shape[1], 3, dtype, max_frames=2, max_pairs=1)
+    st.upload(np.stack([prev, curr]))
+    pkg._cabi.check(L.rbf_set_option(ctx, b"k1_variant", variant), ctx)
+    pkg._cabi.check(L.rbf_set_option(ctx, b"k1_only", 1), ctx)
+    try:
+        res = st.encode([0], [1], thr)[0]
+    finally:
+        L.rbf_set_option(ctx, b"k1_variant", 0)
+        L.rbf_set_option(ctx, b"k1_only", 0)
+    _, _, mask = st.fetch(0)
+    assert res.ones == oones
+    assert np.array_equal(mask.reshape(shape), omask)
+    anyd = (prev != curr).any(axis=2)
+    assert res.resid == int((anyd & (omask == 0)).sum())
+    st.close()
+
+
+# ------------------------------------------------------------------ batched stream (the bench path)
+def _check_stream_vs_oracle(pkg, co, frames, thr, k_over=None):
+    nfr, h, w = frames.shape[:3]
+    st = pkg.FrameStream(h, w, 3, frames.dtype, max_frames=nfr)
+    st.upload(frames)
+    kw = {}
+    n = h * w
+    if k_over is not None:
+        # BASELINE config 5: explicit k*, l = int(p*n*k/ln2)
+        ones = [co.frame_diff_mask(frames[t], frames[t + 1], thr)[1] for t in range(nfr - 1)]
+        kw = dict(k_override=[k_over] * (nfr - 1),
+                  l_override=[int((np.uint64(o) / n) * n * k_over / math.log(2)) for o in ones])
+    res = st.encode_consecutive(nfr, thr, **kw)
+    for t, r in enumerate(res):
+        omask, oones = co.frame_diff_mask(frames[t], frames[t + 1], thr)
+        flat = omask.reshape(-1)
+        over = None if k_over is None else (k_over, kw["l_override"][t])
+        ob, ow, op, on, oratio, ok, ol = co.compress(flat, k_l_override=over)
+        bm, wt, mask = st.fetch(t)
+        assert r.ones == oones and np.array_equal(mask, flat), t
+        assert r.p == op
+        if ok == 0:
+            assert r.raw and r.l == 0
+            continue
+        assert not r.raw and r.l == ol and r.k == ok and r.wlen == len(ow), (t, r, ol, len(ow))
+        assert np.array_equal(bm, np.packbits(ob)), t
+        assert np.array_equal(wt, np.packbits(ow)), t
+    assert not st.decode_verify().any()
+    st.close()
+    return res
+
+
+def test_stream_1080p_mixed_densities(pkg, co):
+    """BASELINE config 2 shape: densities cycle through coded and raw-passthrough branches."""
+    frames = synth_stream(1080, 1920, 7, 2, [0.01, 0.05, 0.15, 0.30, 0.0, 0.40])
+    res = _check_stream_vs_oracle(pkg, co, frames, 3.0)
+    assert [r.raw for r in res] == [False, False, False, False, True, True]
+
+
+def test_stream_small_and_ragged(pkg, co):
+    for (h, w) in [(64, 64), (7, 11), (100, 100), (123, 457)]:
+        frames = synth_stream(h, w, 4, 5, [0.05, 0.2, 0.01])
+        _check_stream_vs_oracle(pkg, co, frames, 3.0)
+
+
+def test_stream_4k_full_size(pkg, co):
+    """BASELINE config 3 frame size, p = 0.05: bit-exact against the C oracle."""
+    frames = synth_stream(2160, 3840, 3, 3, [0.05])
+    res = _check_stream_vs_oracle(pkg, co, frames, 3.0)
+    assert all(1_850_000 < r.l < 1_970_000 for r in res)
+
+
+def test_stream_8k_u16_k_sweep(pkg, co):
+    """BASELINE config 5: 8K 16-bit samples (int16 wrap in the diff), explicit k*."""
+    rng = np.random.default_rng(5)
+    f0 = rng.integers(0, 65536, (4320, 7680, 3)).astype(np.uint16)
+    f1 = f0.copy()
+    ch = rng.random((4320, 7680)) < 0.05
+    f1[ch] = (f1[ch].astype(np.int64) + 16384) % 65536
+    frames = np.stack([f0, f1])
+    for ks in (1.5, 4.0):
+        _check_stream_vs_oracle(pkg, co, frames, 3.0, k_over=ks)
+
+
+def test_stream_properties_at_scale(pkg):
+    """Size-independent properties on a longer 4K stream: decode(encode) == mask, witness >= ones,
+    no false negatives (every set mask bit passes), bitmap fill near 1/2 at the optimal k."""
+    frames = synth_stream(2160, 3840, 9, 11, [0.05, 0.02, 0.1])
+    st = pkg.FrameStream(2160, 3840, 3, np.uint8, max_frames=9)
+    st.upload(frames)
+    res = st.encode_consecutive(9, 3.0)
+    assert not st.decode_verify().any()
+    for t, r in enumerate(res):
+        bm, wt, mask = st.fetch(t)
+        assert r.ones == int(mask.sum()) and r.wlen >= r.ones
+        assert int(np.unpackbits(wt)[:r.wlen].sum()) == r.ones           # witness ones == mask ones
+        fill = np.unpackbits(bm)[:r.l].mean()
+        assert 0.45 < fill < 0.55, fill
+    st.close()
+
+
+# ------------------------------------------------------------------ string API (rbf:9-214)
+def test_string_filters_against_golden(pkg):
+    g = golden_json("strings_kat.json")
+    rng = random.Random(g["items_seed"])
+    items = ["".join(rng.choices("abcdefghijklmnopqrstuvwxyz", k=10)) for _ in range(400)]
+    probes = ["".join(rng.choices("abcdefghijklmnopqrstuvwxyz", k=10)) for _ in range(600)] + items[:50]
+    long_items = ["x" * n + str(n) for n in (0, 1, 31, 32, 33, 63, 64, 65, 200)]
+    for rec in g["filters"]:
+        if rec["kind"] == "rational":
+            f = pkg.RationalBloomFilter(rec["m"], rec["k"])
+            assert f.ceil_k == rec["ceil_k"]
+            for it in items[:5]:
+                f.add(it)                       # one-item signature of the reference
+            f.add_many(items[5:] + long_items)
+        elif rec["kind"] == "standard":
+            f = pkg.StandardBloomFilter(rec["m"], rec["k"])
+            f.add_many(items + long_items)
+        else:
+            continue
+        bits = np.array(f.bit_array, dtype=np.uint8)
+        assert isinstance(f.bit_array, list)
+        assert int(bits.sum()) == rec["bits_set"], rec
+        assert sha(np.packbits(bits)) == rec["bitmap_sha256"], rec
+        res = f.contains_many(probes + long_items).astype(np.uint8)
+        assert int(res.sum()) == rec["contains_true"]
+        assert sha(np.packbits(res)) == rec["contains_sha256"]
+        assert f.contains(items[0]) and all(f.contains(x) for x in long_items)
+    for rec in g["optimal_size"]:
+        assert pkg.RationalBloomFilter.get_optimal_size(rec["n"], rec["p"]) == rec["size"]
+    for rec in g["optimal_hash_count"]:
+        assert float(pkg.RationalBloomFilter.get_optimal_hash_count(rec["m"], rec["n"])).hex() == rec["k"]
+        assert pkg.StandardBloomFilter.get_optimal_hash_count(rec["m"], rec["n"]) == rec["k_std"]
+
+
+# ------------------------------------------------------------------ ImprovedVideoCompressor (ivc:309-523)
+def test_compress_video_roundtrip_gop(pkg, tmp_path):
+    frames = [f for f in synth_stream(96, 160, 12, 21, [0.05, 0.2, 0.0, 0.4])]
+    comp = pkg.ImprovedVideoCompressor(keyframe_interval=5, use_direct_yuv=True)
+    out = str(tmp_path / "clip.bfvc")
+    stats = comp.compress_video(list(frames), output_path=out, input_color_space="YUV")
+    assert set(stats) >= {"frame_count", "original_size", "compressed_size", "compression_ratio", "space_savings",
+                          "compression_time", "frames_per_second", "keyframes", "keyframe_ratio", "output_path",
+                          "color_space", "overall_ratio"}
+    assert stats["frame_count"] == 12 and stats["keyframes"] == 3
+    dec = comp.decompress_video(input_path=out)
+    ver = comp.verify_lossless(frames, dec)
+    assert ver["lossless"] and ver["exact_frame_matches"] == 12
+    assert all(hasattr(f, "yuv_info") for f in dec)
+    with pytest.raises(ValueError):
+        comp.compress_video([])
+    (tmp_path / "bad.bfvc").write_bytes(b"NOPE1234")
+    with pytest.raises(ValueError):
+        comp.decompress_video(input_path=str(tmp_path / "bad.bfvc"))
+
+
+def test_compress_video_all_keyframes_matches_reference_bytes(pkg):
+    g = golden_json("keyframe_kat.json")
+    arr = golden_npz("keyframe_arrays.npz")
+    rec = [r for r in g["cases"] if r["name"] == "bgr_u8"][0]
+    f = arr["bgr_u8/frame"]
+    comp = pkg.ImprovedVideoCompressor(keyframe_interval=1)
+    comp.compress_video([f, f.copy()])
+    assert comp._last_compressed_frames[0] == arr["bgr_u8/payload"].tobytes()
+    assert comp._last_compressed_frames[1] == arr["bgr_u8/payload"].tobytes()
+
+
+def test_compress_video_reference_mode_falls_back_to_keyframe(pkg):
+    frames = [f for f in synth_stream(64, 64, 4, 31, [0.05])]
+    frames[2] = frames[2].copy()
+    frames[2][5, 5, 2] ^= 1                       # chroma-only change: the Y mask cannot carry it (SURVEY hard part 3ii)
+    comp = pkg.ImprovedVideoCompressor(keyframe_interval=30)
+    comp.inter_frame_mode = "reference"
+    comp.inter_frame_threshold = 3.0
+    stats = comp.compress_video(list(frames), input_color_space="YUV")
+    dec = comp.decompress_video(compressed_frames=comp._last_compressed_frames)
+    assert comp.verify_lossless(frames, dec)["lossless"]
+    assert stats["keyframes"] >= 2
