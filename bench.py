@@ -201,6 +201,7 @@ def run_ours(args):
     n = H * W
     pairs = F - 1
     cabi.check(L.rbf_set_option(ctx, b"k1_variant", args.k1_variant), ctx)
+    cabi.check(L.rbf_set_option(ctx, b"query_variant", args.query_variant), ctx)
 
     frames, pin = pinned_array(cabi, (F, H, W, 3))
     fill_stream(frames, seed=3 + 1000 * rank)
@@ -298,7 +299,8 @@ def run_ours(args):
                                    (F, pairs, "; frames sharded per rank + one NCCL all-gather of the bit arrays" if world > 1 else ""),
                        "height": H, "width": W, "frames": F, "pairs_per_gpu": pairs, "parallelism": "frame-sharded x%d" % world,
                        "l2_policy": "inputs larger than L2: %.2f GB of frames per step, no flush needed" % (F * n * 3 / 1e9),
-                       "k1_variant": "tma-bulk-ring" if args.k1_variant == 1 else "ldg128",
+                       "k1_variant": "tma-bulk-ring" if args.k1_variant == 1 else "ldg256",
+                       "query_variant": "staged-queues" if args.query_variant == 1 else "per-lane",
                        "mean_l_bits": float(np.mean([r.l for r in res])), "mean_witness_bits": float(np.mean([r.wlen for r in res]))},
             "roofline": {"bound": "hbm", "kernel": "k_query", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -342,6 +344,7 @@ def main():
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--k1-variant", type=int, default=0)
+    ap.add_argument("--query-variant", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

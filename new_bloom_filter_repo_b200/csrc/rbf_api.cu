@@ -28,6 +28,7 @@ struct rbf_ctx {
     cudaDeviceProp prop;
     int sm_count = 0;
     int k1_variant = 0;
+    int query_variant = 1;  // 1: staged queue-compacted K3, 0: per-lane divergent K3
     int k1_only = 0;        // stop after K1 (mask + counts): VideoFrameCompressor._calculate_frame_diff
     int mask_mode = 0;      // 0: |dY| > thr (ivc:808); 1: additionally any byte of the pixel differs
     int query_smem_cap = 0;
@@ -241,6 +242,7 @@ extern "C" int rbf_device_info(rbf_ctx* c, char* name, int name_len, int* sm_cou
 extern "C" int rbf_set_option(rbf_ctx* c, const char* key, int64_t v) {
     if (!c || !key) return set_err(c, RBF_ERR_INVALID, "rbf_set_option: NULL");
     if (!strcmp(key, "k1_variant")) { c->k1_variant = (int)v; return RBF_OK; }
+    if (!strcmp(key, "query_variant")) { c->query_variant = v ? 1 : 0; return RBF_OK; }
     if (!strcmp(key, "k1_only")) { c->k1_only = v ? 1 : 0; return RBF_OK; }
     if (!strcmp(key, "mask_mode")) { c->mask_mode = v ? 1 : 0; return RBF_OK; }
     if (!strcmp(key, "query_smem_bytes")) {
@@ -443,7 +445,7 @@ extern "C" int rbf_compress_mask(rbf_ctx* c, const uint8_t* mask, uint64_t n, co
     CK(c, cudaMemsetAsync(d_bits, 0, bit_words_padded(l) * 4, c->st));
     CK(c, cudaMemsetAsync(d_wit, 0, mw * 4, c->st));
     LAUNCH(c, launch_insert(d_job, 1, ncent, c->sm_count, c->st));
-    LAUNCH(c, launch_query(d_job, d_prefix, 1, ncent, c->sm_count, c->query_smem_cap, c->st));
+    LAUNCH(c, launch_query(d_job, d_prefix, 1, ncent, (uint32_t)l, c->query_variant, c->sm_count, c->query_smem_cap, c->st));
     LAUNCH(c, launch_witness(d_job, 1, d_cnt + 1, c->st));
     CK(c, cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, c->st)); c->d2h += 16;
     CK(c, cudaStreamSynchronize(c->st));
@@ -499,7 +501,7 @@ extern "C" int rbf_decompress_mask(rbf_ctx* c, const uint8_t* bitmap, uint64_t l
     uint32_t h_prefix[2] = {0, ncent};
     CK(c, cudaMemcpyAsync(d_job, &J, sizeof J, cudaMemcpyHostToDevice, c->st));
     CK(c, cudaMemcpyAsync(d_prefix, h_prefix, 8, cudaMemcpyHostToDevice, c->st));
-    LAUNCH(c, launch_query(d_job, d_prefix, 1, ncent, c->sm_count, c->query_smem_cap, c->st));
+    LAUNCH(c, launch_query(d_job, d_prefix, 1, ncent, (uint32_t)l, c->query_variant, c->sm_count, c->query_smem_cap, c->st));
     LAUNCH(c, launch_expand(d_job, 1, d_cnt, c->st));
     LAUNCH(c, launch_unpack_bits((const uint32_t*)d_out, (uint8_t*)d_bytes, n, c->st));
     uint32_t h_cnt = 0;
@@ -527,7 +529,7 @@ struct rbf_stream {
     FrameJob* h_jobs = nullptr;
     PairJob* h_pairs = nullptr;
     uint32_t *h_prefix = nullptr, *h_ones = nullptr, *h_resid = nullptr, *h_wlen = nullptr;
-    uint32_t last_pairs = 0;
+    uint32_t last_pairs = 0, last_max_l = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool staged = false;
     std::vector<rbf_mask_info> last_infos;
@@ -647,7 +649,7 @@ static int stream_encode_async(rbf_stream* s, const uint32_t* prev_idx, const ui
     CK(c, cudaStreamSynchronize(c->st));               // the one host round trip: (p, k, l, T) need libm's log2
     s->last_infos.assign(pairs, rbf_mask_info());
     const uint32_t ncent = (n + 99u) / 100u;
-    uint32_t total_cent = 0, coded_pairs = 0;
+    uint32_t total_cent = 0, coded_pairs = 0, max_l = 0;
     s->h_prefix[0] = 0;
     for (uint32_t i = 0; i < pairs; i++) {
         rbf_mask_info& in = s->last_infos[i];
@@ -668,12 +670,14 @@ static int stream_encode_async(rbf_stream* s, const uint32_t* prev_idx, const ui
             job_set_filter(J, l, k, *sd);
             in.k = k; in.l = l; in.floor_k = J.floor_k; in.act_T = J.act_T;
             total_cent += ncent; coded_pairs++;
+            if (l > max_l) max_l = (uint32_t)l;
         } else {
             in.raw = 1;
         }
         s->h_prefix[i + 1] = total_cent;
     }
     s->last_pairs = pairs;
+    s->last_max_l = max_l;
     if (coded_pairs == 0 || c->k1_only) return RBF_OK;
     CK(c, cudaMemcpyAsync(s->d_jobs, s->h_jobs, sizeof(FrameJob) * pairs, cudaMemcpyHostToDevice, c->st));
     CK(c, cudaMemcpyAsync(s->d_prefix, s->h_prefix, 4 * ((size_t)pairs + 1), cudaMemcpyHostToDevice, c->st));
@@ -682,7 +686,7 @@ static int stream_encode_async(rbf_stream* s, const uint32_t* prev_idx, const ui
     CK(c, cudaEventRecord(s->ev[2], c->st));
     LAUNCH(c, launch_insert(s->d_jobs, (int)pairs, ncent, c->sm_count, c->st));
     CK(c, cudaEventRecord(s->ev[3], c->st));
-    LAUNCH(c, launch_query(s->d_jobs, s->d_prefix, (int)pairs, total_cent, c->sm_count, c->query_smem_cap, c->st));
+    LAUNCH(c, launch_query(s->d_jobs, s->d_prefix, (int)pairs, total_cent, max_l, c->query_variant, c->sm_count, c->query_smem_cap, c->st));
     CK(c, cudaEventRecord(s->ev[4], c->st));
     LAUNCH(c, launch_witness(s->d_jobs, (int)pairs, s->d_wlen, c->st));
     CK(c, cudaEventRecord(s->ev[5], c->st));
@@ -779,10 +783,11 @@ extern "C" int rbf_stream_decode_verify(rbf_stream* s, uint32_t pairs, uint64_t*
         FrameJob& J = s->h_jobs[i];
         J.out_mask = s->d_dec + (size_t)i * stride_w;
         J.wlen_in = (uint32_t)s->last_infos[i].wlen;
+        J.mask = nullptr;                               // a real decode knows no mask (ivc:286-304)
     }
     CK(c, cudaMemcpyAsync(s->d_jobs, s->h_jobs, sizeof(FrameJob) * pairs, cudaMemcpyHostToDevice, c->st));
     const uint32_t total_cent = s->h_prefix[pairs];
-    LAUNCH(c, launch_query(s->d_jobs, s->d_prefix, (int)pairs, total_cent, c->sm_count, c->query_smem_cap, c->st));
+    LAUNCH(c, launch_query(s->d_jobs, s->d_prefix, (int)pairs, total_cent, s->last_max_l, c->query_variant, c->sm_count, c->query_smem_cap, c->st));
     LAUNCH(c, launch_expand(s->d_jobs, (int)pairs, s->d_wlen, c->st));
     void* d_cnt; int rc;
     if ((rc = scratch_get(c, 7, 4 * (size_t)pairs + 4096, &d_cnt))) return rc;

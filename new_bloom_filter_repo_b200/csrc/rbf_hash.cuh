@@ -176,6 +176,23 @@ RBF_HD uint64_t finish(int kind, uint64_t D, uint64_t seed, uint32_t y) {
     }
 }
 
+
+// Compile-time-kind versions used by the staged query kernel (no switch in the inner loops).
+template <int KIND>
+RBF_HD uint64_t decade_state_t(uint64_t C, uint64_t seed, uint32_t x) {      // hq >= 1 only
+    if (KIND == K_4B) return lane4_fin(seed_h0(seed, 5) ^ (C + (((uint64_t)x * XP1) << 24)));
+    if (KIND == K_8B) return lane8_fin(seed_h0(seed, 9), C + (((uint64_t)x * XP2) << 56));
+    if (KIND == K_44) return C + (((uint64_t)x * XP1) << 16);
+    if (KIND == K_88) return C + (((uint64_t)x * XP2) << 48);
+    return byte_step(C, 48u + x);
+}
+template <int KIND>
+RBF_HD uint64_t finish_t(uint64_t D, uint64_t seed, uint32_t y) {
+    if (KIND == K_44) return avalanche(lane4_fin(seed_h0(seed, 4) ^ (D + (((uint64_t)y * XP1) << 24))));
+    if (KIND == K_88) return avalanche(lane8_fin(seed_h0(seed, 8), D + (((uint64_t)y * XP2) << 56)));
+    return avalanche(byte_step(D, 48u + y));
+}
+
 // ---------------------------------------------------------------------------------
 // h mod m for a per-frame constant m (the Bloom size l).  Barrett with M = floor(2^64/m),
 // truncated partial products: q_est in [Q-3, Q], so r_est = h - q_est*m < 4m fits 32 bits

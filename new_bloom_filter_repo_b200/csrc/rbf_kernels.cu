@@ -110,55 +110,87 @@ __device__ __forceinline__ int absdiff_sample(uint32_t a, uint32_t b) {
     }
 }
 
+// 256-bit streaming load: one 32 B sector per thread per instruction (LDG.E.256 on sm_100a)
+__device__ __forceinline__ void ldg256_stream(const void* p, uint32_t* r) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+
+// Four consecutive 8-bit YUV444 pixels = three 32-bit words per frame.  Byte-SIMD:
+//   nm = 4-bit mask of  |Ya - Yb| > thr  (VABSDIFF4 + per-byte compare),  nd = 4-bit "any byte differs".
+// gt_or / gt_and fold the out-of-range thresholds (thr < 0: always, thr > 254: never) into the compare.
+__device__ __forceinline__ void yuv8_group4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b0, uint32_t b1, uint32_t b2,
+                                            uint32_t thr4, uint32_t gt_or, uint32_t gt_and, uint32_t& nm, uint32_t& nd) {
+    const uint32_t ya = __byte_perm(__byte_perm(a0, a1, 0x0630), a2, 0x5210);   // Y bytes of pixels 0..3
+    const uint32_t yb = __byte_perm(__byte_perm(b0, b1, 0x0630), b2, 0x5210);
+    const uint32_t gt = (__vcmpgtu4(__vabsdiffu4(ya, yb), thr4) & gt_and) | gt_or;
+    nm = ((gt & 0x01010101u) * 0x01020408u) >> 24;
+    const uint32_t x0 = a0 ^ b0, x1 = a1 ^ b1, x2 = a2 ^ b2;
+    const uint32_t f0 = x0 & 0x00ffffffu, f1 = __funnelshift_r(x0, x1, 24) & 0x00ffffffu,
+                   f2 = __funnelshift_r(x1, x2, 16) & 0x00ffffffu, f3 = x2 >> 8;
+    nd = min(f0, 1u) | (min(f1, 1u) << 1) | (min(f2, 1u) << 2) | (min(f3, 1u) << 3);
+}
+
 template <int PB, int S>
 __global__ void __launch_bounds__(256) k_threshold(const PairJob* __restrict__ pairs, uint32_t npix, int thr, int any_mode,
                                                    uint32_t* __restrict__ ones, uint32_t* __restrict__ resid) {
     const PairJob pj = pairs[blockIdx.y];
     const uint32_t nwords = (npix + 31u) >> 5;
     uint32_t cnt_ones = 0, cnt_res = 0;
+    const uint32_t thr4 = (uint32_t)(thr < 0 ? 0 : (thr > 254 ? 254 : thr)) * 0x01010101u;
+    const uint32_t gt_or = thr < 0 ? 0xffffffffu : 0u, gt_and = thr > 254 ? 0u : 0xffffffffu;
+    const uint32_t any_mask = any_mode ? 0xfu : 0u;
     for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += gridDim.x * blockDim.x) {
         const uint32_t px0 = w << 5;
         uint32_t m = 0, r = 0;
         if (px0 + 32u <= npix) {
-            constexpr int NV = 2 * PB;                 // uint4 per 32 pixels
-            constexpr int HV = (NV > 6) ? NV / 2 : NV; // cap registers: at most 6 uint4 per frame in flight
-            constexpr int HALVES = NV / HV;
-            constexpr int PXH = 32 / HALVES;
+            if (PB == 3 && S == 1) {
+                uint32_t A[24], B[24];
+                const uint8_t* pa = pj.prev + (size_t)px0 * 3;
+                const uint8_t* pb = pj.curr + (size_t)px0 * 3;
 #pragma unroll
-            for (int hf = 0; hf < HALVES; hf++) {
-                const uint4* pa = reinterpret_cast<const uint4*>(pj.prev + (size_t)(px0 + hf * PXH) * PB);
-                const uint4* pb = reinterpret_cast<const uint4*>(pj.curr + (size_t)(px0 + hf * PXH) * PB);
-                uint32_t A[4 * HV], B[4 * HV];
+                for (int j = 0; j < 3; j++) ldg256_stream(pa + 32 * j, A + 8 * j);
 #pragma unroll
-                for (int j = 0; j < HV; j++) {
-                    uint4 va = ldg_stream(pa + j);
-                    A[4 * j] = va.x; A[4 * j + 1] = va.y; A[4 * j + 2] = va.z; A[4 * j + 3] = va.w;
+                for (int j = 0; j < 3; j++) ldg256_stream(pb + 32 * j, B + 8 * j);
+#pragma unroll
+                for (int g = 0; g < 8; g++) {
+                    uint32_t nm, nd;
+                    yuv8_group4(A[3 * g], A[3 * g + 1], A[3 * g + 2], B[3 * g], B[3 * g + 1], B[3 * g + 2], thr4, gt_or, gt_and, nm, nd);
+                    nm |= nd & any_mask;
+                    m |= nm << (4 * g);
+                    r |= (nd & ~nm) << (4 * g);
                 }
+            } else {
+                constexpr int NV = PB;                     // 256-bit loads per 32 pixels
+                constexpr int HV = (NV > 3) ? NV / 2 : NV; // at most 3 in flight per frame
+                constexpr int HALVES = NV / HV;
+                constexpr int PXH = 32 / HALVES;
 #pragma unroll
-                for (int j = 0; j < HV; j++) {
-                    uint4 vb = ldg_stream(pb + j);
-                    B[4 * j] = vb.x; B[4 * j + 1] = vb.y; B[4 * j + 2] = vb.z; B[4 * j + 3] = vb.w;
-                }
+                for (int hf = 0; hf < HALVES; hf++) {
+                    uint32_t A[8 * HV], B[8 * HV];
+                    const uint8_t* pa = pj.prev + (size_t)(px0 + hf * PXH) * PB;
+                    const uint8_t* pb = pj.curr + (size_t)(px0 + hf * PXH) * PB;
 #pragma unroll
-                for (int k = 0; k < PXH; k++) {
-                    const int o = k * PB;              // byte offset of the pixel (compile-time)
-                    uint32_t ya, yb;
-                    if (S == 1) {
-                        ya = (A[o >> 2] >> (8 * (o & 3))) & 0xffu;
-                        yb = (B[o >> 2] >> (8 * (o & 3))) & 0xffu;
-                    } else {
-                        ya = (A[o >> 2] >> (8 * (o & 3))) & 0xffffu;
-                        yb = (B[o >> 2] >> (8 * (o & 3))) & 0xffffu;
+                    for (int j = 0; j < HV; j++) ldg256_stream(pa + 32 * j, A + 8 * j);
+#pragma unroll
+                    for (int j = 0; j < HV; j++) ldg256_stream(pb + 32 * j, B + 8 * j);
+#pragma unroll
+                    for (int k = 0; k < PXH; k++) {
+                        const int o = k * PB;              // byte offset of the pixel (compile-time)
+                        const uint32_t smask = (S == 1) ? 0xffu : 0xffffu;
+                        const uint32_t ya = (A[o >> 2] >> (8 * (o & 3))) & smask;
+                        const uint32_t yb = (B[o >> 2] >> (8 * (o & 3))) & smask;
+                        uint32_t anyd = 0;                 // any byte of the pixel differs
+#pragma unroll
+                        for (int q = 0; q < PB; q++) {
+                            const int oq = o + q;
+                            anyd |= ((A[oq >> 2] ^ B[oq >> 2]) >> (8 * (oq & 3))) & 0xffu;
+                        }
+                        const uint32_t bit = ((absdiff_sample<PB, S>(ya, yb) > thr) || (any_mode && anyd != 0u)) ? 1u : 0u;
+                        m |= bit << (hf * PXH + k);
+                        r |= ((anyd != 0u && bit == 0u) ? 1u : 0u) << (hf * PXH + k);
                     }
-                    uint32_t anyd = 0;                 // any byte of the pixel differs
-#pragma unroll
-                    for (int q = 0; q < PB; q++) {
-                        const int oq = o + q;
-                        anyd |= ((A[oq >> 2] ^ B[oq >> 2]) >> (8 * (oq & 3))) & 0xffu;
-                    }
-                    const uint32_t bit = ((absdiff_sample<PB, S>(ya, yb) > thr) || (any_mode && anyd != 0u)) ? 1u : 0u;
-                    m |= bit << (hf * PXH + k);
-                    r |= ((anyd != 0u && bit == 0u) ? 1u : 0u) << (hf * PXH + k);
                 }
             }
         } else {                                        // ragged last word: scalar loads
@@ -198,8 +230,9 @@ __global__ void __launch_bounds__(256) k_threshold(const PairJob* __restrict__ p
 
 // ------------------------------------------------------------------------------------------
 // K1 (TMA variant): persistent CTAs, 4-stage mbarrier ring, one elected thread issues
-// cp.async.bulk copies of a 2 x 12 KB tile (prev, curr); consumers read the Y bytes from
-// shared memory conflict-free (lane stride = PB bytes) and ballot the mask words directly.
+// cp.async.bulk copies of a 2 x 12 KB tile (prev, curr); for 8-bit YUV444 each lane reads
+// four pixels (three words, bank-conflict free) and runs the same byte-SIMD as above; the
+// per-lane nibbles are OR-reduced over 8-lane groups (REDUX) into mask words.
 // ------------------------------------------------------------------------------------------
 constexpr int TMA_STAGES = 4;
 constexpr int TMA_TILE_BYTES = 12288;                  // per frame per stage (4096 px at 3 B/px)
@@ -214,12 +247,14 @@ __global__ void __launch_bounds__(TMA_THREADS) k_threshold_tma(const PairJob* __
     __shared__ __align__(8) uint64_t full[TMA_STAGES];
     uint8_t* bufA = smem;                               // [STAGES][TILE]
     uint8_t* bufB = smem + TMA_STAGES * TMA_TILE_BYTES;
-    const uint32_t full_tiles = npix / TP;              // tiles fully inside a frame (bulk copy needs 16 B multiples)
-    const uint32_t tiles_per_frame = full_tiles;
+    const uint32_t tiles_per_frame = npix / TP;         // full tiles only (bulk copies need 16 B multiples)
     const uint64_t total = (uint64_t)tiles_per_frame * (uint64_t)F;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NWARP = TMA_THREADS / 32;
     constexpr uint32_t WPW = TP / 32 / NWARP;           // mask words per warp per tile
+    const uint32_t thr4 = (uint32_t)(thr < 0 ? 0 : (thr > 254 ? 254 : thr)) * 0x01010101u;
+    const uint32_t gt_or = thr < 0 ? 0xffffffffu : 0u, gt_and = thr > 254 ? 0u : 0xffffffffu;
+    const uint32_t any_mask = any_mode ? 0xfu : 0u;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TMA_STAGES; s++) mbar_init(&full[s], 1);
@@ -243,7 +278,19 @@ __global__ void __launch_bounds__(TMA_THREADS) k_threshold_tma(const PairJob* __
             if (t < total) issue(t, s);
         }
     }
-    uint32_t it = 0;
+    uint32_t it = 0, acc_o = 0, acc_r = 0, acc_f = 0xffffffffu;     // per-thread counts of the current frame
+    auto flush_counts = [&]() {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            acc_o += __shfl_xor_sync(0xffffffffu, acc_o, d);
+            acc_r += __shfl_xor_sync(0xffffffffu, acc_r, d);
+        }
+        if (lane == 0 && acc_f != 0xffffffffu) {
+            if (acc_o) atomicAdd(ones + acc_f, acc_o);
+            if (acc_r) atomicAdd(resid + acc_f, acc_r);
+        }
+        acc_o = 0; acc_r = 0;
+    };
     for (uint64_t t = t0; t < total; t += gridDim.x, it++) {
         const int slot = it % TMA_STAGES;
         const uint32_t parity = (it / TMA_STAGES) & 1u;
@@ -251,37 +298,53 @@ __global__ void __launch_bounds__(TMA_THREADS) k_threshold_tma(const PairJob* __
             uint64_t tn = t + (uint64_t)(TMA_STAGES - 1) * gridDim.x;
             if (tn < total) { fence_proxy_async(); issue(tn, (it + TMA_STAGES - 1) % TMA_STAGES); }
         }
-        mbar_wait(&full[slot], parity);
         const uint32_t f = (uint32_t)(t / tiles_per_frame), ti = (uint32_t)(t % tiles_per_frame);
+        if (f != acc_f) { flush_counts(); acc_f = f; }  // warp-uniform
+        mbar_wait(&full[slot], parity);
         const uint8_t* a = bufA + slot * TMA_TILE_BYTES;
         const uint8_t* b = bufB + slot * TMA_TILE_BYTES;
-        uint32_t myword = 0, c_o = 0, c_r = 0;
-#pragma unroll 4
-        for (uint32_t k = 0; k < WPW; k++) {
-            const uint32_t px = (warp * WPW + k) * 32u + lane;
-            const uint8_t* pa = a + px * PB;
-            const uint8_t* pb = b + px * PB;
-            uint32_t ya, yb, anyd = 0;
-            if (S == 1) { ya = pa[0]; yb = pb[0]; }
-            else { ya = *reinterpret_cast<const uint16_t*>(pa); yb = *reinterpret_cast<const uint16_t*>(pb); }
-#pragma unroll
-            for (int q = 0; q < PB; q += S) {
-                if (S == 1) anyd |= (uint32_t)(pa[q] ^ pb[q]);
-                else anyd |= (uint32_t)(*reinterpret_cast<const uint16_t*>(pa + q) ^ *reinterpret_cast<const uint16_t*>(pb + q));
+        uint32_t* mask_out = pairs[f].mask + (size_t)ti * (TP / 32) + warp * WPW;
+        if (PB == 3 && S == 1) {
+            const uint32_t* a32 = reinterpret_cast<const uint32_t*>(a) + (size_t)warp * WPW * 24;   // 32 px = 24 words
+            const uint32_t* b32 = reinterpret_cast<const uint32_t*>(b) + (size_t)warp * WPW * 24;
+#pragma unroll 2
+            for (uint32_t k = 0; k < WPW / 4; k++) {      // 128 pixels (4 mask words) per iteration
+                const uint32_t o = (k * 32u + lane) * 3u;
+                uint32_t nm, nd;
+                yuv8_group4(a32[o], a32[o + 1], a32[o + 2], b32[o], b32[o + 1], b32[o + 2], thr4, gt_or, gt_and, nm, nd);
+                nm |= nd & any_mask;
+                const uint32_t nr = nd & ~nm;
+                const uint32_t grp = 0xffu << (lane & 24);
+                const uint32_t wm = __reduce_or_sync(grp, nm << (4 * (lane & 7)));
+                const uint32_t wr = __reduce_or_sync(grp, nr << (4 * (lane & 7)));
+                if ((lane & 7) == 0) { mask_out[k * 4 + (lane >> 3)] = wm; acc_o += __popc(wm); acc_r += __popc(wr); }
             }
-            const bool bit = (absdiff_sample<PB, S>(ya, yb) > thr) || (any_mode && anyd != 0u);
-            const uint32_t bm = __ballot_sync(0xffffffffu, bit);
-            const uint32_t br = __ballot_sync(0xffffffffu, (!bit) && anyd != 0u);
-            if (lane == (int)k) myword = bm;
-            c_o += __popc(bm); c_r += __popc(br);      // identical in every lane
-        }
-        if (lane < (int)WPW) pairs[f].mask[(size_t)ti * (TP / 32) + warp * WPW + lane] = myword;
-        if (lane == 0) {
-            if (c_o) atomicAdd(ones + f, c_o);
-            if (c_r) atomicAdd(resid + f, c_r);
+        } else {
+            uint32_t myword = 0;
+#pragma unroll 4
+            for (uint32_t k = 0; k < WPW; k++) {
+                const uint32_t px = (warp * WPW + k) * 32u + lane;
+                const uint8_t* pa = a + px * PB;
+                const uint8_t* pb = b + px * PB;
+                uint32_t ya, yb, anyd = 0;
+                if (S == 1) { ya = pa[0]; yb = pb[0]; }
+                else { ya = *reinterpret_cast<const uint16_t*>(pa); yb = *reinterpret_cast<const uint16_t*>(pb); }
+#pragma unroll
+                for (int q = 0; q < PB; q += S) {
+                    if (S == 1) anyd |= (uint32_t)(pa[q] ^ pb[q]);
+                    else anyd |= (uint32_t)(*reinterpret_cast<const uint16_t*>(pa + q) ^ *reinterpret_cast<const uint16_t*>(pb + q));
+                }
+                const bool bit = (absdiff_sample<PB, S>(ya, yb) > thr) || (any_mode && anyd != 0u);
+                const uint32_t bm = __ballot_sync(0xffffffffu, bit);
+                const uint32_t br = __ballot_sync(0xffffffffu, (!bit) && anyd != 0u);
+                if (lane == (int)k) myword = bm;
+                if (lane == 0) { acc_o += __popc(bm); acc_r += __popc(br); }
+            }
+            if (lane < (int)WPW) mask_out[lane] = myword;
         }
         __syncthreads();                                // slot may be refilled next iteration
     }
+    flush_counts();
 }
 
 // remainder of each frame after the last full TMA tile: same maths with guarded scalar loads
@@ -467,6 +530,188 @@ __global__ void __launch_bounds__(QT) k_query(const FrameJob* __restrict__ jobs,
         for (uint32_t c = c_begin + threadIdx.x; c < c_end; c += QT) {
             const Bits128 r = query_century(bv, K, c, min(100u, J.n - 100u * c));
             pass4[c] = make_uint4((uint32_t)r.lo, (uint32_t)(r.lo >> 32), (uint32_t)r.hi, (uint32_t)(r.hi >> 32));
+        }
+        g = seg_end;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 (staged): the same query as a warp-synchronous pipeline of DENSE stages.
+//
+// check_index is a pure conjunction (ivc:127-136), so its probes may be evaluated in any order
+// and abandoned at the first zero.  Lane t of a warp owns century slab+t; the warp walks the
+// 100 positions of its 32 centuries in lockstep:
+//   stage A  (all positions)        h1 -> probe 0.  ~1/2 survive (the Bloom fill is ~1/2).
+//   stage B  (survivors of A)       h2 -> probes 1..floor_k-1.
+//   stage C  (survivors of B)       activation hash -> the floor_k+1'th probe if activated.
+// Survivors are compacted through per-warp shared-memory rings (ballot + popc), so stages B and C
+// always run with 32 busy lanes instead of diverging per lane.  A stage-B record carries the
+// owner's decade state of seed 2; stage C fetches the owner's century state of the activation
+// seed with a shuffle.  Positions whose mask bit is set are known to pass (a Bloom filter has no
+// false negatives) and skip the hashing.  Results are identical to the per-lane form above.
+// ------------------------------------------------------------------------------------------
+constexpr int Q2_WARPS = 16;
+constexpr int Q2_THREADS = Q2_WARPS * 32;
+constexpr int Q2_RING = 64;                               // entries per ring (two drains' worth)
+constexpr int Q2_WARP_WORDS = (Q2_RING * 16 + Q2_RING * 8 + 32 * 16) / 4;   // B ring, C ring, pass accumulators
+
+template <bool HYBRID>
+__device__ __forceinline__ uint32_t test_bit_t(const uint32_t* __restrict__ sm, const uint32_t* __restrict__ gl,
+                                               uint32_t sm_words, uint32_t idx) {
+    const uint32_t w = idx >> 5;
+    uint32_t word;
+    if (HYBRID) word = (w < sm_words) ? sm[w] : __ldg(gl + w);
+    else word = sm[w];
+    return (word >> (idx & 31u)) & 1u;
+}
+
+__device__ __forceinline__ void deliver_pass(uint32_t* pacc, uint32_t tag) {
+    const uint32_t owner = tag >> 8, pos = 10u * ((tag >> 4) & 15u) + (tag & 15u);
+    atomicOr(pacc + owner * 4u + (pos >> 5), 1u << (pos & 31u));
+}
+
+template <int KIND, bool HYBRID>
+__device__ __noinline__ void query_slab_staged(const FilterK K, const uint32_t* __restrict__ sm,
+                                               const uint32_t* __restrict__ gl, uint32_t sm_words,
+                                               const uint32_t* __restrict__ mask, uint32_t n, uint32_t slab_c0,
+                                               uint32_t c_end, uint4* __restrict__ pass4, uint4* qb, uint2* qc,
+                                               uint32_t* pacc) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t c = slab_c0 + lane;
+    const bool active = c < c_end;
+    const Century cen = make_century(active ? c : slab_c0);
+    const uint64_t C1 = century_state(cen, K.s1), C2 = century_state(cen, K.s2), CA = century_state(cen, K.sA);
+    const uint32_t nvalid = active ? min(100u, n - 100u * c) : 0u;
+    Bits128 mb; mb.lo = 0; mb.hi = 0;
+    if (active && mask != nullptr) mb = load_bits100(mask, c, nvalid);
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t qb_head = 0, qb_cnt = 0, qc_head = 0, qc_cnt = 0;
+    uint64_t D1 = 0, D2 = 0;
+    for (uint32_t step = 0;; step++) {
+        const bool feeding = step < 100u;
+        if (feeding) {                                                   // ---- stage A: one position per lane
+            const uint32_t x = step / 10u, y = step - 10u * x;
+            if (y == 0u) { D1 = decade_state_t<KIND>(C1, K.s1, x); D2 = decade_state_t<KIND>(C2, K.s2, x); }
+            const uint32_t idx0 = mod_u64(finish_t<KIND>(D1, K.s1, y), K.fm);
+            const uint32_t mbit = (step < 64u) ? ((uint32_t)(mb.lo >> step) & 1u) : ((uint32_t)(mb.hi >> (step - 64u)) & 1u);
+            const bool sv = (step < nvalid) && (mbit == 0u) && (test_bit_t<HYBRID>(sm, gl, sm_words, idx0) != 0u);
+            const uint32_t b = __ballot_sync(0xffffffffu, sv);
+            if (sv) qb[(qb_head + qb_cnt + __popc(b & lt)) & (Q2_RING - 1)] =
+                        make_uint4(idx0, (lane << 8) | (x << 4) | y, (uint32_t)D2, (uint32_t)(D2 >> 32));
+            qb_cnt += __popc(b);
+        }
+        if (qb_cnt >= 32u || (!feeding && qb_cnt > 0u)) {                // ---- stage B: 32 survivors of A
+            __syncwarp();
+            const uint32_t nb = min(32u, qb_cnt);
+            const bool have = lane < nb;
+            const uint4 r = qb[(qb_head + lane) & (Q2_RING - 1)];
+            qb_head = (qb_head + nb) & (Q2_RING - 1);
+            qb_cnt -= nb;
+            const uint32_t stepm = mod_u64(finish_t<KIND>((uint64_t)r.z | ((uint64_t)r.w << 32), K.s2, r.y & 15u), K.fm);
+            uint32_t idx = have ? r.x : 0u;
+            bool ok = have;
+            for (uint32_t i = 1; i < K.fk; i++) {
+                idx = addmod(idx, have ? stepm : 0u, K.fm.m);
+                ok = ok && (test_bit_t<HYBRID>(sm, gl, sm_words, idx) != 0u);
+                if (!__any_sync(0xffffffffu, ok)) break;
+            }
+            if (K.has_act) {
+                idx = addmod(idx, have ? stepm : 0u, K.fm.m);           // index of probe floor_k
+                const uint32_t b2 = __ballot_sync(0xffffffffu, ok);
+                if (ok) qc[(qc_head + qc_cnt + __popc(b2 & lt)) & (Q2_RING - 1)] = make_uint2(idx, r.y);
+                qc_cnt += __popc(b2);
+            } else if (ok) {
+                deliver_pass(pacc, r.y);
+            }
+        }
+        if (qc_cnt >= 32u || (!feeding && qb_cnt == 0u && qc_cnt > 0u)) { // ---- stage C: 32 survivors of B
+            __syncwarp();
+            const uint32_t nc = min(32u, qc_cnt);
+            const bool have = lane < nc;
+            const uint2 r = qc[(qc_head + lane) & (Q2_RING - 1)];
+            qc_head = (qc_head + nc) & (Q2_RING - 1);
+            qc_cnt -= nc;
+            const uint32_t tag = have ? r.y : 0u;
+            const uint32_t owner = tag >> 8;
+            const uint64_t CAo = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)CA, owner) |
+                                 ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(CA >> 32), owner) << 32);
+            const uint64_t hA = finish_t<KIND>(decade_state_t<KIND>(CAo, K.sA, (tag >> 4) & 15u), K.sA, tag & 15u);
+            bool ok = have;
+            if (hA < K.T) ok = ok && (test_bit_t<HYBRID>(sm, gl, sm_words, have ? r.x : 0u) != 0u);
+            if (ok) deliver_pass(pacc, tag);
+        }
+        if (!feeding && qb_cnt == 0u && qc_cnt == 0u) break;
+    }
+    __syncwarp();
+    uint4 acc = *reinterpret_cast<uint4*>(pacc + lane * 4u);
+    *reinterpret_cast<uint4*>(pacc + lane * 4u) = make_uint4(0, 0, 0, 0);
+    if (active) {
+        acc.x |= (uint32_t)mb.lo; acc.y |= (uint32_t)(mb.lo >> 32); acc.z |= (uint32_t)mb.hi; acc.w |= (uint32_t)(mb.hi >> 32);
+        pass4[c] = acc;
+    }
+    __syncwarp();
+}
+
+template <bool HYBRID>
+__global__ void __launch_bounds__(Q2_THREADS, 1) k_query2(const FrameJob* __restrict__ jobs,
+                                                          const uint32_t* __restrict__ cent_prefix, int F,
+                                                          uint32_t smem_words_cap) {
+    extern __shared__ __align__(128) uint32_t dyn[];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    uint32_t* wq = dyn + warp * Q2_WARP_WORDS;
+    uint4* qb = reinterpret_cast<uint4*>(wq);
+    uint2* qc = reinterpret_cast<uint2*>(wq + Q2_RING * 4);
+    uint32_t* pacc = wq + Q2_RING * 4 + Q2_RING * 2;
+    uint32_t* sbits = dyn + Q2_WARPS * Q2_WARP_WORDS;
+    *reinterpret_cast<uint4*>(pacc + lane * 4u) = make_uint4(0, 0, 0, 0);
+    const uint32_t total = cent_prefix[F];
+    const uint32_t lo = (uint32_t)(((uint64_t)total * blockIdx.x) / gridDim.x);
+    const uint32_t hi = (uint32_t)(((uint64_t)total * (blockIdx.x + 1)) / gridDim.x);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (lo >= hi) return;
+    int f = 0;
+    { int a = 0, b = F; while (a < b) { int m = (a + b) >> 1; if (cent_prefix[m + 1] > lo) b = m; else a = m + 1; } f = a; }
+    uint32_t parity = 0, g = lo;
+    while (g < hi) {
+        while (cent_prefix[f + 1] <= g) f++;
+        const FrameJob& J = jobs[f];
+        const uint32_t seg_end = min(hi, cent_prefix[f + 1]);
+        const uint32_t c_begin = g - cent_prefix[f], c_end = seg_end - cent_prefix[f];
+        const uint32_t nwords = (J.l + 31u) >> 5;
+        const uint32_t sw = min((nwords + 3u) & ~3u, smem_words_cap);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&bar, sw * 4u);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(J.bits);
+            uint8_t* dst = reinterpret_cast<uint8_t*>(sbits);
+            for (uint32_t off = 0; off < sw * 4u; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, sw * 4u - off), &bar);
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+        const FilterK K = filter_consts(J);
+        uint4* pass4 = reinterpret_cast<uint4*>(J.pass);
+        for (uint32_t slab = c_begin + 32u * warp; slab < c_end; slab += 32u * Q2_WARPS) {
+            const uint32_t last = min(slab + 31u, c_end - 1u);
+            const bool uniform = slab >= 1u && ndigits_u32(slab) == ndigits_u32(last) && K.fk >= 1u;
+            if (uniform) {
+                switch (make_century(slab).kind) {
+                case K_4B: query_slab_staged<K_4B, HYBRID>(K, sbits, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_8B: query_slab_staged<K_8B, HYBRID>(K, sbits, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_44: query_slab_staged<K_44, HYBRID>(K, sbits, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_88: query_slab_staged<K_88, HYBRID>(K, sbits, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                default:   query_slab_staged<K_BB, HYBRID>(K, sbits, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                }
+            } else {                                    // century 0, a digit-count boundary, or floor_k == 0
+                const uint32_t c = slab + lane;
+                if (c < c_end) {
+                    BitView bv; bv.sm = sbits; bv.gl = J.bits; bv.sm_words = sw;
+                    const Bits128 r = query_century(bv, K, c, min(100u, J.n - 100u * c));
+                    pass4[c] = make_uint4((uint32_t)r.lo, (uint32_t)(r.lo >> 32), (uint32_t)r.hi, (uint32_t)(r.hi >> 32));
+                }
+            }
         }
         g = seg_end;
     }
@@ -777,11 +1022,36 @@ cudaError_t launch_insert(const FrameJob* d_jobs, int F, uint32_t max_centuries,
 
 int query_max_smem_bytes() { return 232448 - 1024; }    // 227 KB opt-in minus static shared memory + slack
 
+template <bool HYBRID>
+static cudaError_t launch_query2_t(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, int F, uint32_t total_centuries,
+                                   int sm_count, int smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(k_query2<HYBRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    uint32_t grid = (uint32_t)sm_count;
+    const uint32_t max_useful = (total_centuries + Q2_THREADS - 1) / Q2_THREADS;
+    if (grid > max_useful) grid = max_useful;
+    if (grid < 1u) grid = 1u;
+    k_query2<HYBRID><<<grid, Q2_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F,
+                                                     (uint32_t)((smem - Q2_WARPS * Q2_WARP_WORDS * 4) / 4));
+    return cudaGetLastError();
+}
+
 cudaError_t launch_query(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, int F, uint32_t total_centuries,
-                         int sm_count, int smem_bytes_cap, cudaStream_t st) {
+                         uint32_t max_l_bits, int variant, int sm_count, int smem_bytes_cap, cudaStream_t st) {
     if (F <= 0 || total_centuries == 0) return cudaSuccess;
-    int smem = smem_bytes_cap & ~15;
-    if (smem > query_max_smem_bytes()) smem = query_max_smem_bytes() & ~15;
+    int cap = smem_bytes_cap & ~15;
+    if (cap > query_max_smem_bytes()) cap = query_max_smem_bytes() & ~15;
+    const uint32_t need_words = (((max_l_bits + 31u) >> 5) + 3u) & ~3u;
+    if (variant == 1) {                                   // staged, queue-compacted kernel
+        const int qbytes = Q2_WARPS * Q2_WARP_WORDS * 4;
+        if (cap < qbytes + 1024) cap = qbytes + 1024;
+        const int bits_cap = cap - qbytes;
+        const bool hybrid = (size_t)need_words * 4 > (size_t)bits_cap;
+        const int smem = qbytes + (hybrid ? bits_cap : (int)(need_words * 4 < 16 ? 16 : need_words * 4));
+        return hybrid ? launch_query2_t<true>(d_jobs, d_cent_prefix, F, total_centuries, sm_count, smem, st)
+                      : launch_query2_t<false>(d_jobs, d_cent_prefix, F, total_centuries, sm_count, smem, st);
+    }
+    int smem = (size_t)need_words * 4 > (size_t)cap ? cap : (int)(need_words * 4);
     if (smem < 16) smem = 16;
     cudaError_t e = cudaFuncSetAttribute(k_query, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;

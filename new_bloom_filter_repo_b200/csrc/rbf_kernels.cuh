@@ -42,7 +42,7 @@ cudaError_t launch_threshold(const PairJob* d_pairs, int F, uint32_t npix, int c
                              cudaStream_t st);
 cudaError_t launch_insert(const FrameJob* d_jobs, int F, uint32_t max_centuries, int sm_count, cudaStream_t st);
 cudaError_t launch_query(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, int F, uint32_t total_centuries,
-                         int sm_count, int smem_bytes_cap, cudaStream_t st);
+                         uint32_t max_l_bits, int variant, int sm_count, int smem_bytes_cap, cudaStream_t st);
 cudaError_t launch_witness(const FrameJob* d_jobs, int F, uint32_t* d_wlen, cudaStream_t st);
 cudaError_t launch_expand(const FrameJob* d_jobs, int F, uint32_t* d_consumed, cudaStream_t st);
 cudaError_t launch_bitrev(uint32_t* d_words, size_t nwords, cudaStream_t st);
