@@ -555,27 +555,70 @@ constexpr int Q2_THREADS = Q2_WARPS * 32;
 constexpr int Q2_RING = 64;                               // entries per ring (two drains' worth)
 constexpr int Q2_WARP_WORDS = (Q2_RING * 16 + Q2_RING * 8 + 32 * 16) / 4;   // B ring, C ring, pass accumulators
 
+// explicit shared-space accesses (32-bit shared addresses): no generic-pointer resolution in the hot loops
+__device__ __forceinline__ void sts128_if(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, bool p) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %5, 0;\n @q st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n}" ::"r"(addr), "r"(a), "r"(b),
+                 "r"(c), "r"(d), "r"((uint32_t)p)
+                 : "memory");
+}
+__device__ __forceinline__ void sts64_if(uint32_t addr, uint32_t a, uint32_t b, bool p) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %3, 0;\n @q st.shared.v2.u32 [%0], {%1,%2};\n}" ::"r"(addr), "r"(a), "r"(b),
+                 "r"((uint32_t)p)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_or_shared_if(uint32_t addr, uint32_t v, bool p) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q red.shared.or.b32 [%0], %1;\n}" ::"r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
+}
+
+// bit `idx` of the Bloom array: words [0, sm_words) from shared memory, the rest through L2 (read-only path)
 template <bool HYBRID>
-__device__ __forceinline__ uint32_t test_bit_t(const uint32_t* __restrict__ sm, const uint32_t* __restrict__ gl,
-                                               uint32_t sm_words, uint32_t idx) {
+__device__ __forceinline__ uint32_t probe_bit(uint32_t sm_addr, const uint32_t* __restrict__ gl, uint32_t sm_words, uint32_t idx) {
     const uint32_t w = idx >> 5;
     uint32_t word;
-    if (HYBRID) word = (w < sm_words) ? sm[w] : __ldg(gl + w);
-    else word = sm[w];
+    if (HYBRID) {
+        asm("{\n .reg .pred q;\n setp.lt.u32 q, %1, %2;\n @q ld.shared.u32 %0, [%3];\n @!q ld.global.nc.u32 %0, [%4];\n}"
+            : "=r"(word)
+            : "r"(w), "r"(sm_words), "r"(sm_addr + 4u * w), "l"(gl + w));
+    } else {
+        asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(sm_addr + 4u * w));
+    }
     return (word >> (idx & 31u)) & 1u;
 }
 
-__device__ __forceinline__ void deliver_pass(uint32_t* pacc, uint32_t tag) {
+// fast reductions for 2 <= m <= 2^30 (the staged kernel is only launched then)
+__device__ __forceinline__ uint32_t mod_fast(uint64_t h, const FastMod& f) {
+    const uint32_t hh = (uint32_t)(h >> 32), hl = (uint32_t)h;
+    const uint32_t q = hh * f.Mh + __umulhi(hh, f.Ml) + __umulhi(hl, f.Mh);
+    uint32_t r = hl - q * f.m;
+    r = min(r, r - 2u * f.m);
+    return min(r, r - f.m);
+}
+__device__ __forceinline__ uint32_t addmod_fast(uint32_t a, uint32_t b, uint32_t m) {
+    const uint32_t s = a + b;
+    return min(s, s - m);
+}
+
+// pass bit of (owner lane, x, y) into the owner's 128-bit accumulator
+__device__ __forceinline__ void deliver_pass(uint32_t pacc_addr, uint32_t tag, bool p) {
     const uint32_t owner = tag >> 8, pos = 10u * ((tag >> 4) & 15u) + (tag & 15u);
-    atomicOr(pacc + owner * 4u + (pos >> 5), 1u << (pos & 31u));
+    red_or_shared_if(pacc_addr + 16u * owner + 4u * (pos >> 5), 1u << (pos & 31u), p);
 }
 
 template <int KIND, bool HYBRID>
-__device__ __noinline__ void query_slab_staged(const FilterK K, const uint32_t* __restrict__ sm,
-                                               const uint32_t* __restrict__ gl, uint32_t sm_words,
-                                               const uint32_t* __restrict__ mask, uint32_t n, uint32_t slab_c0,
-                                               uint32_t c_end, uint4* __restrict__ pass4, uint4* qb, uint2* qc,
-                                               uint32_t* pacc) {
+__device__ __noinline__ void query_slab_staged(const FilterK K, uint32_t sm_addr, const uint32_t* __restrict__ gl,
+                                               uint32_t sm_words, const uint32_t* __restrict__ mask, uint32_t n,
+                                               uint32_t slab_c0, uint32_t c_end, uint4* __restrict__ pass4,
+                                               uint32_t qb_addr, uint32_t qc_addr, uint32_t pacc_addr) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t c = slab_c0 + lane;
     const bool active = c < c_end;
@@ -584,67 +627,93 @@ __device__ __noinline__ void query_slab_staged(const FilterK K, const uint32_t* 
     const uint32_t nvalid = active ? min(100u, n - 100u * c) : 0u;
     Bits128 mb; mb.lo = 0; mb.hi = 0;
     if (active && mask != nullptr) mb = load_bits100(mask, c, nvalid);
+    // positions that need no hashing: known members (mask bit set) and positions beyond n
+    uint64_t skip_lo = mb.lo, skip_hi = mb.hi;
+    if (nvalid < 64u) { skip_hi = ~0ull; skip_lo |= ~((1ull << nvalid) - 1ull); }
+    else skip_hi |= ~((1ull << (nvalid - 64u)) - 1ull);
     const uint32_t lt = (1u << lane) - 1u;
-    uint32_t qb_head = 0, qb_cnt = 0, qc_head = 0, qc_cnt = 0;
-    uint64_t D1 = 0, D2 = 0;
-    for (uint32_t step = 0;; step++) {
-        const bool feeding = step < 100u;
-        if (feeding) {                                                   // ---- stage A: one position per lane
-            const uint32_t x = step / 10u, y = step - 10u * x;
-            if (y == 0u) { D1 = decade_state_t<KIND>(C1, K.s1, x); D2 = decade_state_t<KIND>(C2, K.s2, x); }
-            const uint32_t idx0 = mod_u64(finish_t<KIND>(D1, K.s1, y), K.fm);
-            const uint32_t mbit = (step < 64u) ? ((uint32_t)(mb.lo >> step) & 1u) : ((uint32_t)(mb.hi >> (step - 64u)) & 1u);
-            const bool sv = (step < nvalid) && (mbit == 0u) && (test_bit_t<HYBRID>(sm, gl, sm_words, idx0) != 0u);
-            const uint32_t b = __ballot_sync(0xffffffffu, sv);
-            if (sv) qb[(qb_head + qb_cnt + __popc(b & lt)) & (Q2_RING - 1)] =
-                        make_uint4(idx0, (lane << 8) | (x << 4) | y, (uint32_t)D2, (uint32_t)(D2 >> 32));
-            qb_cnt += __popc(b);
+    const uint32_t lane_tag = lane << 8;
+    uint32_t qb_head = 0, qb_cnt = 0, qc_head = 0, qc_cnt = 0;      // warp-uniform ring state
+#pragma unroll 1
+    for (uint32_t x = 0; x <= 10u; x++) {                            // x == 10: drain what is left
+        const bool feeding = x < 10u;
+        uint64_t D1 = 0, D2 = 0;
+        uint32_t skip10 = 0x3ffu;
+        if (feeding) {
+            D1 = decade_state_t<KIND>(C1, K.s1, x);
+            D2 = decade_state_t<KIND>(C2, K.s2, x);
+            const uint32_t p0 = 10u * x;                             // bits [p0, p0+10) of the 128-bit skip set
+            const uint64_t sh = (p0 < 64u) ? ((skip_lo >> p0) | (p0 ? (skip_hi << (64u - p0)) : 0ull)) : (skip_hi >> (p0 - 64u));
+            skip10 = (uint32_t)sh & 0x3ffu;
         }
-        if (qb_cnt >= 32u || (!feeding && qb_cnt > 0u)) {                // ---- stage B: 32 survivors of A
-            __syncwarp();
-            const uint32_t nb = min(32u, qb_cnt);
-            const bool have = lane < nb;
-            const uint4 r = qb[(qb_head + lane) & (Q2_RING - 1)];
-            qb_head = (qb_head + nb) & (Q2_RING - 1);
-            qb_cnt -= nb;
-            const uint32_t stepm = mod_u64(finish_t<KIND>((uint64_t)r.z | ((uint64_t)r.w << 32), K.s2, r.y & 15u), K.fm);
-            uint32_t idx = have ? r.x : 0u;
-            bool ok = have;
-            for (uint32_t i = 1; i < K.fk; i++) {
-                idx = addmod(idx, have ? stepm : 0u, K.fm.m);
-                ok = ok && (test_bit_t<HYBRID>(sm, gl, sm_words, idx) != 0u);
-                if (!__any_sync(0xffffffffu, ok)) break;
+#pragma unroll 1
+        for (uint32_t y = 0; y < 10u; y += 2u) {
+            uint32_t idxA = 0, idxB = 0;
+            bool svA = false, svB = false;
+            if (feeding) {                                           // ---- stage A: two positions per lane (ILP)
+                idxA = mod_fast(finish_t<KIND>(D1, K.s1, y), K.fm);
+                idxB = mod_fast(finish_t<KIND>(D1, K.s1, y + 1u), K.fm);
+                const uint32_t bA = probe_bit<HYBRID>(sm_addr, gl, sm_words, idxA);
+                const uint32_t bB = probe_bit<HYBRID>(sm_addr, gl, sm_words, idxB);
+                svA = (bA & ~(skip10 >> y) & 1u) != 0u;
+                svB = (bB & ~(skip10 >> (y + 1u)) & 1u) != 0u;
             }
-            if (K.has_act) {
-                idx = addmod(idx, have ? stepm : 0u, K.fm.m);           // index of probe floor_k
-                const uint32_t b2 = __ballot_sync(0xffffffffu, ok);
-                if (ok) qc[(qc_head + qc_cnt + __popc(b2 & lt)) & (Q2_RING - 1)] = make_uint2(idx, r.y);
-                qc_cnt += __popc(b2);
-            } else if (ok) {
-                deliver_pass(pacc, r.y);
+#pragma unroll 1
+            for (uint32_t j = 0; j < 2u; j++) {
+                if (feeding) {                                       // push survivors of A into ring B
+                    const bool sv = j ? svB : svA;
+                    const uint32_t b = __ballot_sync(0xffffffffu, sv);
+                    const uint32_t slot = (qb_head + qb_cnt + __popc(b & lt)) & (Q2_RING - 1);
+                    sts128_if(qb_addr + 16u * slot, j ? idxB : idxA, lane_tag | (x << 4) | (y + j), (uint32_t)D2,
+                              (uint32_t)(D2 >> 32), sv);
+                    qb_cnt += __popc(b);
+                }
+                if (qb_cnt >= 32u || (!feeding && qb_cnt > 0u)) {    // ---- stage B: 32 survivors of A
+                    __syncwarp();
+                    const uint32_t nb = min(32u, qb_cnt);
+                    const bool have = lane < nb;
+                    const uint4 r = lds128(qb_addr + 16u * ((qb_head + lane) & (Q2_RING - 1)));
+                    qb_head = (qb_head + nb) & (Q2_RING - 1);
+                    qb_cnt -= nb;
+                    const uint32_t stepm = have ? mod_fast(finish_t<KIND>((uint64_t)r.z | ((uint64_t)r.w << 32), K.s2, r.y & 15u), K.fm) : 0u;
+                    uint32_t idx = have ? r.x : 0u;
+                    bool ok = have;
+                    for (uint32_t i = 1; i < K.fk; i++) {
+                        idx = addmod_fast(idx, stepm, K.fm.m);
+                        ok = ok && (probe_bit<HYBRID>(sm_addr, gl, sm_words, idx) != 0u);
+                        if (!__any_sync(0xffffffffu, ok)) break;
+                    }
+                    if (K.has_act) {
+                        idx = addmod_fast(idx, stepm, K.fm.m);       // index of probe floor_k
+                        const uint32_t b2 = __ballot_sync(0xffffffffu, ok);
+                        sts64_if(qc_addr + 8u * ((qc_head + qc_cnt + __popc(b2 & lt)) & (Q2_RING - 1)), idx, r.y, ok);
+                        qc_cnt += __popc(b2);
+                    } else {
+                        deliver_pass(pacc_addr, r.y, ok);
+                    }
+                }
+                if (qc_cnt >= 32u || (!feeding && qb_cnt == 0u && qc_cnt > 0u)) {   // ---- stage C: 32 survivors of B
+                    __syncwarp();
+                    const uint32_t nc = min(32u, qc_cnt);
+                    const bool have = lane < nc;
+                    const uint2 r = lds64(qc_addr + 8u * ((qc_head + lane) & (Q2_RING - 1)));
+                    qc_head = (qc_head + nc) & (Q2_RING - 1);
+                    qc_cnt -= nc;
+                    const uint32_t tag = have ? r.y : 0u;
+                    const uint32_t owner = tag >> 8;
+                    const uint64_t CAo = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)CA, owner) |
+                                         ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(CA >> 32), owner) << 32);
+                    const uint64_t hA = finish_t<KIND>(decade_state_t<KIND>(CAo, K.sA, (tag >> 4) & 15u), K.sA, tag & 15u);
+                    const uint32_t pb = probe_bit<HYBRID>(sm_addr, gl, sm_words, have ? r.x : 0u);
+                    deliver_pass(pacc_addr, tag, have && (!(hA < K.T) || pb != 0u));
+                }
             }
+            if (!feeding && qb_cnt == 0u && qc_cnt == 0u) break;
         }
-        if (qc_cnt >= 32u || (!feeding && qb_cnt == 0u && qc_cnt > 0u)) { // ---- stage C: 32 survivors of B
-            __syncwarp();
-            const uint32_t nc = min(32u, qc_cnt);
-            const bool have = lane < nc;
-            const uint2 r = qc[(qc_head + lane) & (Q2_RING - 1)];
-            qc_head = (qc_head + nc) & (Q2_RING - 1);
-            qc_cnt -= nc;
-            const uint32_t tag = have ? r.y : 0u;
-            const uint32_t owner = tag >> 8;
-            const uint64_t CAo = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)CA, owner) |
-                                 ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(CA >> 32), owner) << 32);
-            const uint64_t hA = finish_t<KIND>(decade_state_t<KIND>(CAo, K.sA, (tag >> 4) & 15u), K.sA, tag & 15u);
-            bool ok = have;
-            if (hA < K.T) ok = ok && (test_bit_t<HYBRID>(sm, gl, sm_words, have ? r.x : 0u) != 0u);
-            if (ok) deliver_pass(pacc, tag);
-        }
-        if (!feeding && qb_cnt == 0u && qc_cnt == 0u) break;
     }
     __syncwarp();
-    uint4 acc = *reinterpret_cast<uint4*>(pacc + lane * 4u);
-    *reinterpret_cast<uint4*>(pacc + lane * 4u) = make_uint4(0, 0, 0, 0);
+    uint4 acc = lds128(pacc_addr + 16u * lane);
+    sts128_if(pacc_addr + 16u * lane, 0u, 0u, 0u, 0u, true);
     if (active) {
         acc.x |= (uint32_t)mb.lo; acc.y |= (uint32_t)(mb.lo >> 32); acc.z |= (uint32_t)mb.hi; acc.w |= (uint32_t)(mb.hi >> 32);
         pass4[c] = acc;
@@ -660,11 +729,10 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_query2(const FrameJob* __rest
     __shared__ __align__(8) uint64_t bar;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     uint32_t* wq = dyn + warp * Q2_WARP_WORDS;
-    uint4* qb = reinterpret_cast<uint4*>(wq);
-    uint2* qc = reinterpret_cast<uint2*>(wq + Q2_RING * 4);
-    uint32_t* pacc = wq + Q2_RING * 4 + Q2_RING * 2;
+    const uint32_t qb = smem_u32(wq), qc = smem_u32(wq + Q2_RING * 4), pacc = smem_u32(wq + Q2_RING * 4 + Q2_RING * 2);
     uint32_t* sbits = dyn + Q2_WARPS * Q2_WARP_WORDS;
-    *reinterpret_cast<uint4*>(pacc + lane * 4u) = make_uint4(0, 0, 0, 0);
+    const uint32_t sb_addr = smem_u32(sbits);
+    sts128_if(pacc + 16u * lane, 0u, 0u, 0u, 0u, true);
     const uint32_t total = cent_prefix[F];
     const uint32_t lo = (uint32_t)(((uint64_t)total * blockIdx.x) / gridDim.x);
     const uint32_t hi = (uint32_t)(((uint64_t)total * (blockIdx.x + 1)) / gridDim.x);
@@ -695,14 +763,14 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_query2(const FrameJob* __rest
         uint4* pass4 = reinterpret_cast<uint4*>(J.pass);
         for (uint32_t slab = c_begin + 32u * warp; slab < c_end; slab += 32u * Q2_WARPS) {
             const uint32_t last = min(slab + 31u, c_end - 1u);
-            const bool uniform = slab >= 1u && ndigits_u32(slab) == ndigits_u32(last) && K.fk >= 1u;
+            const bool uniform = slab >= 1u && ndigits_u32(slab) == ndigits_u32(last) && K.fk >= 1u && K.fm.fast;
             if (uniform) {
                 switch (make_century(slab).kind) {
-                case K_4B: query_slab_staged<K_4B, HYBRID>(K, sbits, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                case K_8B: query_slab_staged<K_8B, HYBRID>(K, sbits, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                case K_44: query_slab_staged<K_44, HYBRID>(K, sbits, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                case K_88: query_slab_staged<K_88, HYBRID>(K, sbits, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                default:   query_slab_staged<K_BB, HYBRID>(K, sbits, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_4B: query_slab_staged<K_4B, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_8B: query_slab_staged<K_8B, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_44: query_slab_staged<K_44, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_88: query_slab_staged<K_88, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                default:   query_slab_staged<K_BB, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
                 }
             } else {                                    // century 0, a digit-count boundary, or floor_k == 0
                 const uint32_t c = slab + lane;
