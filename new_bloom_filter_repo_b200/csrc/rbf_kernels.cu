@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(QT) k_query(const FrameJob* __restrict__ jobs,
 // seed with a shuffle.  Positions whose mask bit is set are known to pass (a Bloom filter has no
 // false negatives) and skip the hashing.  Results are identical to the per-lane form above.
 // ------------------------------------------------------------------------------------------
-constexpr int Q2_WARPS = 16;
+constexpr int Q2_WARPS = 24;
 constexpr int Q2_THREADS = Q2_WARPS * 32;
 constexpr int Q2_RING = 64;                               // entries per ring (two drains' worth)
 constexpr int Q2_WARP_WORDS = (Q2_RING * 16 + Q2_RING * 8 + 32 * 16) / 4;   // B ring, C ring, pass accumulators
@@ -614,7 +614,65 @@ __device__ __forceinline__ void deliver_pass(uint32_t pacc_addr, uint32_t tag, b
     red_or_shared_if(pacc_addr + 16u * owner + 4u * (pos >> 5), 1u << (pos & 31u), p);
 }
 
-template <int KIND, bool HYBRID>
+struct RingState {                 // warp-uniform
+    uint32_t qb_head, qb_cnt, qc_head, qc_cnt;
+};
+
+// stage B (32 survivors of A) and stage C (32 survivors of B); `force` drains partial batches
+template <int KIND, int FKT, bool HYBRID>
+__device__ __forceinline__ void drain_stages(const FilterK& K, uint32_t sm_addr, const uint32_t* __restrict__ gl,
+                                             uint32_t sm_words, uint32_t qb_addr, uint32_t qc_addr, uint32_t pacc_addr,
+                                             uint32_t lane, uint32_t lt, uint64_t CA, RingState& R, bool force) {
+    if (R.qb_cnt >= 32u || (force && R.qb_cnt > 0u)) {               // ---- stage B
+        __syncwarp();
+        const uint32_t nb = min(32u, R.qb_cnt);
+        const bool have = lane < nb;
+        const uint4 r = lds128(qb_addr + 16u * ((R.qb_head + lane) & (Q2_RING - 1)));
+        R.qb_head = (R.qb_head + nb) & (Q2_RING - 1);
+        R.qb_cnt -= nb;
+        const uint32_t stepm = have ? mod_fast(finish_t<KIND>((uint64_t)r.z | ((uint64_t)r.w << 32), K.s2, r.y & 15u), K.fm) : 0u;
+        uint32_t idx = have ? r.x : 0u;
+        uint32_t ok = have ? 1u : 0u;
+        if (FKT > 0) {                                               // floor_k known at compile time: straight-line probes
+#pragma unroll
+            for (int i = 1; i < FKT; i++) {
+                idx = addmod_fast(idx, stepm, K.fm.m);
+                ok &= probe_bit<HYBRID>(sm_addr, gl, sm_words, idx);
+            }
+        } else {
+            for (uint32_t i = 1; i < K.fk; i++) {
+                idx = addmod_fast(idx, stepm, K.fm.m);
+                ok &= probe_bit<HYBRID>(sm_addr, gl, sm_words, idx);
+                if (!__any_sync(0xffffffffu, ok != 0u)) break;
+            }
+        }
+        if (K.has_act) {
+            idx = addmod_fast(idx, stepm, K.fm.m);                   // index of probe floor_k
+            const uint32_t b2 = __ballot_sync(0xffffffffu, ok != 0u);
+            sts64_if(qc_addr + 8u * ((R.qc_head + R.qc_cnt + __popc(b2 & lt)) & (Q2_RING - 1)), idx, r.y, ok != 0u);
+            R.qc_cnt += __popc(b2);
+        } else {
+            deliver_pass(pacc_addr, r.y, ok != 0u);
+        }
+    }
+    if (R.qc_cnt >= 32u || (force && R.qb_cnt == 0u && R.qc_cnt > 0u)) {   // ---- stage C
+        __syncwarp();
+        const uint32_t nc = min(32u, R.qc_cnt);
+        const bool have = lane < nc;
+        const uint2 r = lds64(qc_addr + 8u * ((R.qc_head + lane) & (Q2_RING - 1)));
+        R.qc_head = (R.qc_head + nc) & (Q2_RING - 1);
+        R.qc_cnt -= nc;
+        const uint32_t tag = have ? r.y : 0u;
+        const uint32_t owner = tag >> 8;
+        const uint64_t CAo = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)CA, owner) |
+                             ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(CA >> 32), owner) << 32);
+        const uint64_t hA = finish_t<KIND>(decade_state_t<KIND>(CAo, K.sA, (tag >> 4) & 15u), K.sA, tag & 15u);
+        const uint32_t pb = probe_bit<HYBRID>(sm_addr, gl, sm_words, have ? r.x : 0u);
+        deliver_pass(pacc_addr, tag, have && (!(hA < K.T) || pb != 0u));
+    }
+}
+
+template <int KIND, int FKT, bool HYBRID>
 __device__ __noinline__ void query_slab_staged(const FilterK K, uint32_t sm_addr, const uint32_t* __restrict__ gl,
                                                uint32_t sm_words, const uint32_t* __restrict__ mask, uint32_t n,
                                                uint32_t slab_c0, uint32_t c_end, uint4* __restrict__ pass4,
@@ -632,85 +690,37 @@ __device__ __noinline__ void query_slab_staged(const FilterK K, uint32_t sm_addr
     if (nvalid < 64u) { skip_hi = ~0ull; skip_lo |= ~((1ull << nvalid) - 1ull); }
     else skip_hi |= ~((1ull << (nvalid - 64u)) - 1ull);
     const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t lane_tag = lane << 8;
-    uint32_t qb_head = 0, qb_cnt = 0, qc_head = 0, qc_cnt = 0;      // warp-uniform ring state
+    RingState R; R.qb_head = 0; R.qb_cnt = 0; R.qc_head = 0; R.qc_cnt = 0;
 #pragma unroll 1
-    for (uint32_t x = 0; x <= 10u; x++) {                            // x == 10: drain what is left
-        const bool feeding = x < 10u;
-        uint64_t D1 = 0, D2 = 0;
-        uint32_t skip10 = 0x3ffu;
-        if (feeding) {
-            D1 = decade_state_t<KIND>(C1, K.s1, x);
-            D2 = decade_state_t<KIND>(C2, K.s2, x);
-            const uint32_t p0 = 10u * x;                             // bits [p0, p0+10) of the 128-bit skip set
-            const uint64_t sh = (p0 < 64u) ? ((skip_lo >> p0) | (p0 ? (skip_hi << (64u - p0)) : 0ull)) : (skip_hi >> (p0 - 64u));
-            skip10 = (uint32_t)sh & 0x3ffu;
-        }
+    for (uint32_t x = 0; x < 10u; x++) {
+        const uint64_t D1 = decade_state_t<KIND>(C1, K.s1, x);
+        const uint64_t D2 = decade_state_t<KIND>(C2, K.s2, x);
+        const uint32_t p0 = 10u * x;                                 // bits [p0, p0+10) of the 128-bit skip set
+        const uint64_t sh = (p0 < 64u) ? ((skip_lo >> p0) | (p0 ? (skip_hi << (64u - p0)) : 0ull)) : (skip_hi >> (p0 - 64u));
+        const uint32_t skip10 = (uint32_t)sh & 0x3ffu;
+        const uint32_t tagx = (lane << 8) | (x << 4);
 #pragma unroll 1
-        for (uint32_t y = 0; y < 10u; y += 2u) {
-            uint32_t idxA = 0, idxB = 0;
-            bool svA = false, svB = false;
-            if (feeding) {                                           // ---- stage A: two positions per lane (ILP)
-                idxA = mod_fast(finish_t<KIND>(D1, K.s1, y), K.fm);
-                idxB = mod_fast(finish_t<KIND>(D1, K.s1, y + 1u), K.fm);
-                const uint32_t bA = probe_bit<HYBRID>(sm_addr, gl, sm_words, idxA);
-                const uint32_t bB = probe_bit<HYBRID>(sm_addr, gl, sm_words, idxB);
-                svA = (bA & ~(skip10 >> y) & 1u) != 0u;
-                svB = (bB & ~(skip10 >> (y + 1u)) & 1u) != 0u;
+        for (uint32_t y = 0; y < 10u; y += 2u) {                     // ---- stage A: two positions per lane (ILP)
+            const uint32_t idxA = mod_fast(finish_t<KIND>(D1, K.s1, y), K.fm);
+            const uint32_t idxB = mod_fast(finish_t<KIND>(D1, K.s1, y + 1u), K.fm);
+            const uint32_t bA = probe_bit<HYBRID>(sm_addr, gl, sm_words, idxA);
+            const uint32_t bB = probe_bit<HYBRID>(sm_addr, gl, sm_words, idxB);
+            const bool svA = (bA & ~(skip10 >> y) & 1u) != 0u;
+            const bool svB = (bB & ~(skip10 >> (y + 1u)) & 1u) != 0u;
+#pragma unroll 1
+            for (uint32_t j = 0; j < 2u; j++) {                      // push survivors, then run B / C when a batch is ready
+                const bool sv = j ? svB : svA;
+                const uint32_t b = __ballot_sync(0xffffffffu, sv);
+                sts128_if(qb_addr + 16u * ((R.qb_head + R.qb_cnt + __popc(b & lt)) & (Q2_RING - 1)), j ? idxB : idxA,
+                          tagx | (y + j), (uint32_t)D2, (uint32_t)(D2 >> 32), sv);
+                R.qb_cnt += __popc(b);
+                drain_stages<KIND, FKT, HYBRID>(K, sm_addr, gl, sm_words, qb_addr, qc_addr, pacc_addr, lane, lt, CA, R, false);
             }
-#pragma unroll 1
-            for (uint32_t j = 0; j < 2u; j++) {
-                if (feeding) {                                       // push survivors of A into ring B
-                    const bool sv = j ? svB : svA;
-                    const uint32_t b = __ballot_sync(0xffffffffu, sv);
-                    const uint32_t slot = (qb_head + qb_cnt + __popc(b & lt)) & (Q2_RING - 1);
-                    sts128_if(qb_addr + 16u * slot, j ? idxB : idxA, lane_tag | (x << 4) | (y + j), (uint32_t)D2,
-                              (uint32_t)(D2 >> 32), sv);
-                    qb_cnt += __popc(b);
-                }
-                if (qb_cnt >= 32u || (!feeding && qb_cnt > 0u)) {    // ---- stage B: 32 survivors of A
-                    __syncwarp();
-                    const uint32_t nb = min(32u, qb_cnt);
-                    const bool have = lane < nb;
-                    const uint4 r = lds128(qb_addr + 16u * ((qb_head + lane) & (Q2_RING - 1)));
-                    qb_head = (qb_head + nb) & (Q2_RING - 1);
-                    qb_cnt -= nb;
-                    const uint32_t stepm = have ? mod_fast(finish_t<KIND>((uint64_t)r.z | ((uint64_t)r.w << 32), K.s2, r.y & 15u), K.fm) : 0u;
-                    uint32_t idx = have ? r.x : 0u;
-                    bool ok = have;
-                    for (uint32_t i = 1; i < K.fk; i++) {
-                        idx = addmod_fast(idx, stepm, K.fm.m);
-                        ok = ok && (probe_bit<HYBRID>(sm_addr, gl, sm_words, idx) != 0u);
-                        if (!__any_sync(0xffffffffu, ok)) break;
-                    }
-                    if (K.has_act) {
-                        idx = addmod_fast(idx, stepm, K.fm.m);       // index of probe floor_k
-                        const uint32_t b2 = __ballot_sync(0xffffffffu, ok);
-                        sts64_if(qc_addr + 8u * ((qc_head + qc_cnt + __popc(b2 & lt)) & (Q2_RING - 1)), idx, r.y, ok);
-                        qc_cnt += __popc(b2);
-                    } else {
-                        deliver_pass(pacc_addr, r.y, ok);
-                    }
-                }
-                if (qc_cnt >= 32u || (!feeding && qb_cnt == 0u && qc_cnt > 0u)) {   // ---- stage C: 32 survivors of B
-                    __syncwarp();
-                    const uint32_t nc = min(32u, qc_cnt);
-                    const bool have = lane < nc;
-                    const uint2 r = lds64(qc_addr + 8u * ((qc_head + lane) & (Q2_RING - 1)));
-                    qc_head = (qc_head + nc) & (Q2_RING - 1);
-                    qc_cnt -= nc;
-                    const uint32_t tag = have ? r.y : 0u;
-                    const uint32_t owner = tag >> 8;
-                    const uint64_t CAo = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)CA, owner) |
-                                         ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(CA >> 32), owner) << 32);
-                    const uint64_t hA = finish_t<KIND>(decade_state_t<KIND>(CAo, K.sA, (tag >> 4) & 15u), K.sA, tag & 15u);
-                    const uint32_t pb = probe_bit<HYBRID>(sm_addr, gl, sm_words, have ? r.x : 0u);
-                    deliver_pass(pacc_addr, tag, have && (!(hA < K.T) || pb != 0u));
-                }
-            }
-            if (!feeding && qb_cnt == 0u && qc_cnt == 0u) break;
         }
     }
+#pragma unroll 1
+    while (R.qb_cnt | R.qc_cnt)                                      // end of the slab: drain what is left
+        drain_stages<KIND, FKT, HYBRID>(K, sm_addr, gl, sm_words, qb_addr, qc_addr, pacc_addr, lane, lt, CA, R, true);
     __syncwarp();
     uint4 acc = lds128(pacc_addr + 16u * lane);
     sts128_if(pacc_addr + 16u * lane, 0u, 0u, 0u, 0u, true);
@@ -719,6 +729,16 @@ __device__ __noinline__ void query_slab_staged(const FilterK K, uint32_t sm_addr
         pass4[c] = acc;
     }
     __syncwarp();
+}
+
+template <int KIND, bool HYBRID>
+__device__ __forceinline__ void query_slab_dispatch(const FilterK& K, uint32_t sm_addr, const uint32_t* __restrict__ gl,
+                                                    uint32_t sm_words, const uint32_t* __restrict__ mask, uint32_t n,
+                                                    uint32_t slab_c0, uint32_t c_end, uint4* __restrict__ pass4, uint32_t qb,
+                                                    uint32_t qc, uint32_t pacc) {
+    if (K.fk == 3u) query_slab_staged<KIND, 3, HYBRID>(K, sm_addr, gl, sm_words, mask, n, slab_c0, c_end, pass4, qb, qc, pacc);
+    else if (K.fk == 2u) query_slab_staged<KIND, 2, HYBRID>(K, sm_addr, gl, sm_words, mask, n, slab_c0, c_end, pass4, qb, qc, pacc);
+    else query_slab_staged<KIND, 0, HYBRID>(K, sm_addr, gl, sm_words, mask, n, slab_c0, c_end, pass4, qb, qc, pacc);
 }
 
 template <bool HYBRID>
@@ -766,11 +786,11 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_query2(const FrameJob* __rest
             const bool uniform = slab >= 1u && ndigits_u32(slab) == ndigits_u32(last) && K.fk >= 1u && K.fm.fast;
             if (uniform) {
                 switch (make_century(slab).kind) {
-                case K_4B: query_slab_staged<K_4B, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                case K_8B: query_slab_staged<K_8B, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                case K_44: query_slab_staged<K_44, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                case K_88: query_slab_staged<K_88, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                default:   query_slab_staged<K_BB, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_4B: query_slab_dispatch<K_4B, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_8B: query_slab_dispatch<K_8B, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_44: query_slab_dispatch<K_44, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_88: query_slab_dispatch<K_88, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                default:   query_slab_dispatch<K_BB, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
                 }
             } else {                                    // century 0, a digit-count boundary, or floor_k == 0
                 const uint32_t c = slab + lane;
