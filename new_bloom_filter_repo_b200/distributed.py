@@ -22,19 +22,39 @@ def shard_pairs(pairs: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def init_nccl_from_torch(dist) -> None:
-    """Create the library's NCCL communicator; the 128-byte unique id travels over torch.distributed."""
-    rank, world = dist.get_rank(), dist.get_world_size()
+def broadcast_unique_id(dist, make_id) -> np.ndarray:
+    """Rank 0 calls make_id() -> uint8[128]; every rank returns the same 128 bytes (torch.distributed broadcast)."""
     import torch
     ident = np.zeros(128, dtype=np.uint8)
-    if rank == 0:
-        _cabi.check(_cabi.lib().rbf_nccl_unique_id(_cabi.ptr(ident)))
-    t = torch.from_numpy(ident)
+    if dist.get_rank() == 0:
+        ident[:] = make_id()
+    t = torch.from_numpy(ident.copy())
     if dist.get_backend() == "nccl":
         t = t.cuda()
     dist.broadcast(t, src=0)
-    ident = t.cpu().numpy().copy()
-    _cabi.check(_cabi.lib().rbf_nccl_init(_cabi.ctx(), _cabi.ptr(ident), rank, world), _cabi.ctx())
+    return t.cpu().numpy().copy()
+
+
+def agree_slot_bytes(dist, local_max_bits: int, align: int = 16) -> int:
+    """Fixed all-gather slot: max over ranks of ceil(l/8), rounded up (every rank must use the same size)."""
+    import torch
+    t = torch.tensor([(int(local_max_bits) + 7) // 8], dtype=torch.int64)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return (int(t.item()) + align - 1) // align * align
+
+
+def _nccl_unique_id() -> np.ndarray:
+    ident = np.zeros(128, dtype=np.uint8)
+    _cabi.check(_cabi.lib().rbf_nccl_unique_id(_cabi.ptr(ident)))
+    return ident
+
+
+def init_nccl_from_torch(dist) -> None:
+    """Create the library's NCCL communicator; the 128-byte unique id travels over torch.distributed."""
+    ident = broadcast_unique_id(dist, _nccl_unique_id)
+    _cabi.check(_cabi.lib().rbf_nccl_init(_cabi.ctx(), _cabi.ptr(ident), dist.get_rank(), dist.get_world_size()), _cabi.ctx())
 
 
 class DeviceBuffer:

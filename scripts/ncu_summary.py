@@ -1,0 +1,29 @@
+import csv, sys, collections, subprocess
+rep, kern = sys.argv[1], sys.argv[2]
+raw = subprocess.run(["ncu","-i",rep,"--page","raw","--csv"],capture_output=True,text=True).stdout
+rows=list(csv.reader(raw.splitlines())); hdr=rows[0]
+want=['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','smsp__inst_executed.sum','sm__warps_active.avg.pct_of_peak_sustained_active','launch__registers_per_thread','launch__grid_size','launch__block_size','smsp__issue_active.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active','l1tex__throughput.avg.pct_of_peak_sustained_elapsed','lts__throughput.avg.pct_of_peak_sustained_elapsed','smsp__thread_inst_executed_per_inst_executed.ratio','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum','smsp__warp_issue_stalled_no_instruction_per_warp_active.pct']
+for r in rows[2:]:
+    if kern in r[hdr.index('Kernel Name')]:
+        for w in want:
+            if w in hdr: print('  ',w,'=',r[hdr.index(w)])
+        break
+src = subprocess.run(["ncu","-i",rep,"--page","source","--csv","--kernel-name","regex:"+kern],capture_output=True,text=True).stdout
+rows=list(csv.reader(src.splitlines()))
+hi=[i for i,r in enumerate(rows) if r and r[0]=='Address'][0]
+hdr=rows[hi]; data=[r for r in rows[hi+1:] if len(r)==len(hdr) and r[0]!='Address']
+ia=hdr.index('Instructions Executed'); ts=hdr.index('Thread Instructions Executed'); sc=hdr.index('Source'); ss=hdr.index('# Samples')
+tot=sum(int(r[ia]) for r in data); tott=sum(int(r[ts]) for r in data); totsamp=sum(int(r[ss]) for r in data)
+print('sass instrs',len(data),'warp-instr',tot,'thread-instr',tott,'samples',totsamp)
+ops=collections.Counter(); samp=collections.Counter()
+for r in data:
+    t=r[sc].split(); op=(t[1] if t[0].startswith('@') else t[0]).split('.')[0]
+    ops[op]+=int(r[ia]); samp[op]+=int(r[ss])
+for op,c in ops.most_common(18): print('   %-10s %6.2f%% inst   %6.2f%% samples'%(op,100*c/tot,100*samp[op]/totsamp))
+# stall breakdown
+stalls=[h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
+tots={h:sum(int(r[hdr.index(h)] or 0) for r in data) for h in stalls}
+print({k:v for k,v in sorted(tots.items(), key=lambda kv:-kv[1])[:10]})
+# hottest instructions by samples
+top=sorted(data,key=lambda r:-int(r[ss]))[:25]
+for r in top: print('   ',r[ss],r[ia],r[sc][:90])

@@ -354,3 +354,27 @@ def test_compress_video_reference_mode_falls_back_to_keyframe(pkg):
     dec = comp.decompress_video(compressed_frames=comp._last_compressed_frames)
     assert comp.verify_lossless(frames, dec)["lossless"]
     assert stats["keyframes"] >= 2
+
+
+# ------------------------------------------------------------------ NCCL all-gather path (single rank here; N > 1 in bench.py)
+def test_nccl_allgather_single_rank(pkg):
+    import ctypes as C
+    from new_bloom_filter_repo_b200 import distributed as rdist
+    cabi = pkg._cabi
+    frames = synth_stream(270, 480, 5, 41, [0.05, 0.1])
+    st = pkg.FrameStream(270, 480, 3, np.uint8, max_frames=5)
+    st.upload(frames)
+    res = st.encode_consecutive(5, 3.0)
+    ident = np.zeros(128, dtype=np.uint8)
+    cabi.check(cabi.lib().rbf_nccl_unique_id(cabi.ptr(ident)))
+    cabi.check(cabi.lib().rbf_nccl_init(cabi.ctx(), cabi.ptr(ident), 0, 1), cabi.ctx())
+    slot = (max((r.l + 7) // 8 for r in res) + 15) // 16 * 16
+    send, recv = rdist.allgather_bitmaps(st, 4, slot, 1)
+    cabi.check(cabi.lib().rbf_sync(cabi.ctx()), cabi.ctx())
+    got = recv.to_host().reshape(4, slot)
+    for t, r in enumerate(res):
+        bm, _, _ = st.fetch(t, want_mask=False)
+        assert np.array_equal(got[t, : len(bm)], bm)
+    send.free(); recv.free()
+    cabi.check(cabi.lib().rbf_nccl_destroy(cabi.ctx()), cabi.ctx())
+    st.close()
