@@ -28,6 +28,7 @@ struct rbf_ctx {
     cudaDeviceProp prop;
     int sm_count = 0;
     int k1_variant = 0;
+    int insert_variant = 1; // 1: dense warp-compacted K2, 0: per-lane K2
     int query_variant = 1;  // 1: staged queue-compacted K3, 0: per-lane divergent K3
     int k1_only = 0;        // stop after K1 (mask + counts): VideoFrameCompressor._calculate_frame_diff
     int mask_mode = 0;      // 0: |dY| > thr (ivc:808); 1: additionally any byte of the pixel differs
@@ -243,6 +244,7 @@ extern "C" int rbf_set_option(rbf_ctx* c, const char* key, int64_t v) {
     if (!c || !key) return set_err(c, RBF_ERR_INVALID, "rbf_set_option: NULL");
     if (!strcmp(key, "k1_variant")) { c->k1_variant = (int)v; return RBF_OK; }
     if (!strcmp(key, "query_variant")) { c->query_variant = v ? 1 : 0; return RBF_OK; }
+    if (!strcmp(key, "insert_variant")) { c->insert_variant = v ? 1 : 0; return RBF_OK; }
     if (!strcmp(key, "k1_only")) { c->k1_only = v ? 1 : 0; return RBF_OK; }
     if (!strcmp(key, "mask_mode")) { c->mask_mode = v ? 1 : 0; return RBF_OK; }
     if (!strcmp(key, "query_smem_bytes")) {
@@ -444,7 +446,7 @@ extern "C" int rbf_compress_mask(rbf_ctx* c, const uint8_t* mask, uint64_t n, co
     CK(c, cudaMemcpyAsync(d_prefix, h_prefix, 8, cudaMemcpyHostToDevice, c->st));
     CK(c, cudaMemsetAsync(d_bits, 0, bit_words_padded(l) * 4, c->st));
     CK(c, cudaMemsetAsync(d_wit, 0, mw * 4, c->st));
-    LAUNCH(c, launch_insert(d_job, 1, ncent, c->sm_count, c->st));
+    LAUNCH(c, launch_insert(d_job, 1, ncent, c->insert_variant, c->sm_count, c->st));
     LAUNCH(c, launch_query(d_job, d_prefix, 1, ncent, (uint32_t)l, c->query_variant, c->sm_count, c->query_smem_cap, c->st));
     LAUNCH(c, launch_witness(d_job, 1, d_cnt + 1, c->st));
     CK(c, cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, c->st)); c->d2h += 16;
@@ -684,7 +686,7 @@ static int stream_encode_async(rbf_stream* s, const uint32_t* prev_idx, const ui
     CK(c, cudaMemsetAsync(s->d_bits, 0, s->mask_stride_w * 4 * pairs, c->st));
     CK(c, cudaMemsetAsync(s->d_wit, 0, s->mask_stride_w * 4 * pairs, c->st));
     CK(c, cudaEventRecord(s->ev[2], c->st));
-    LAUNCH(c, launch_insert(s->d_jobs, (int)pairs, ncent, c->sm_count, c->st));
+    LAUNCH(c, launch_insert(s->d_jobs, (int)pairs, ncent, c->insert_variant, c->sm_count, c->st));
     CK(c, cudaEventRecord(s->ev[3], c->st));
     LAUNCH(c, launch_query(s->d_jobs, s->d_prefix, (int)pairs, total_cent, max_l, c->query_variant, c->sm_count, c->query_smem_cap, c->st));
     CK(c, cudaEventRecord(s->ev[4], c->st));

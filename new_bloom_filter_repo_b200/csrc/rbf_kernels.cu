@@ -53,6 +53,11 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {   // read-once fra
     return r;
 }
 
+// fire-and-forget bit set in a global bit array (RED.OR, no return value -> no round trip to wait for)
+__device__ __forceinline__ void red_or_global(uint32_t* addr, uint32_t v) {
+    asm volatile("red.global.or.b32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // 100-bit helpers (a "century" of positions)
 // ------------------------------------------------------------------------------------------
@@ -85,11 +90,11 @@ __device__ __forceinline__ void or_bits128(uint32_t* __restrict__ W, uint64_t bi
     uint32_t s0 = (uint32_t)lo, s1 = (uint32_t)(lo >> 32), s2 = (uint32_t)hi, s3 = (uint32_t)(hi >> 32);
     uint32_t o0 = s0 << sh, o1 = __funnelshift_l(s0, s1, sh), o2 = __funnelshift_l(s1, s2, sh),
              o3 = __funnelshift_l(s2, s3, sh), o4 = __funnelshift_l(s3, 0u, sh);
-    if (o0) atomicOr(W + w, o0);
-    if (o1) atomicOr(W + w + 1, o1);
-    if (o2) atomicOr(W + w + 2, o2);
-    if (o3) atomicOr(W + w + 3, o3);
-    if (o4) atomicOr(W + w + 4, o4);
+    if (o0) red_or_global(W + w, o0);
+    if (o1) red_or_global(W + w + 1, o1);
+    if (o2) red_or_global(W + w + 2, o2);
+    if (o3) red_or_global(W + w + 3, o3);
+    if (o4) red_or_global(W + w + 4, o4);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -392,10 +397,10 @@ __device__ __forceinline__ void insert_hashes(uint32_t* __restrict__ bits, const
     uint32_t idx = mod_u64(h1, K.fm);
     const uint32_t step = mod_u64(h2, K.fm);
     for (uint32_t i = 0; i < K.fk; i++) {
-        atomicOr(bits + (idx >> 5), 1u << (idx & 31u));
+        red_or_global(bits + (idx >> 5), 1u << (idx & 31u));
         idx = addmod(idx, step, K.fm.m);
     }
-    if (K.has_act && hA < K.T) atomicOr(bits + (idx >> 5), 1u << (idx & 31u));
+    if (K.has_act && hA < K.T) red_or_global(bits + (idx >> 5), 1u << (idx & 31u));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -423,6 +428,103 @@ __global__ void __launch_bounds__(256) k_insert(const FrameJob* __restrict__ job
                 const uint64_t h2 = finish(cen.kind, decade_state(cen, C2, K.s2, x), K.s2, y);
                 const uint64_t hA = K.has_act ? finish(cen.kind, decade_state(cen, CA, K.sA, x), K.sA, y) : 0ull;
                 insert_hashes(J.bits, K, h1, h2, hA);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 (dense): the same insert with all lanes busy.  The mask is sparse (p ~ 5 %), so a lane
+// looping over its own set positions leaves most of the warp idle.  Here a warp takes a slab of
+// 32 centuries: every lane publishes its three century states to shared memory, the set
+// positions of the slab are compacted (count, warp scan, scatter) into a per-warp item list, and
+// the list is consumed 32 items at a time: two-character finish from the owner's century state,
+// Barrett reduction, RED.OR into the bit array.
+// ------------------------------------------------------------------------------------------
+constexpr int I2_WARPS = 4;
+constexpr int I2_LIST = 3200;                                        // worst case: every position of the slab set
+
+template <int KIND>
+__device__ __forceinline__ void insert_slab_dense(const FilterK& K, uint32_t* __restrict__ bits, const Bits128 mb,
+                                                  const Century& cen, uint64_t* cs, uint16_t* list, uint32_t lane) {
+    cs[lane * 3 + 0] = century_state(cen, K.s1);
+    cs[lane * 3 + 1] = century_state(cen, K.s2);
+    cs[lane * 3 + 2] = century_state(cen, K.sA);
+    const uint32_t cnt = __popcll(mb.lo) + __popcll(mb.hi);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    uint32_t off = inc - cnt;
+    uint64_t v = mb.lo;
+    while (v) { list[off++] = (uint16_t)((lane << 7) | (uint32_t)(__ffsll((long long)v) - 1)); v &= v - 1ull; }
+    v = mb.hi;
+    while (v) { list[off++] = (uint16_t)((lane << 7) | (uint32_t)(__ffsll((long long)v) + 63)); v &= v - 1ull; }
+    __syncwarp();
+    for (uint32_t base = 0; base < total; base += 32u) {
+        const uint32_t i = base + lane;
+        if (i < total) {
+            const uint32_t tag = list[i];
+            const uint32_t owner = tag >> 7, pos = tag & 127u, x = pos / 10u, y = pos - 10u * x;
+            const uint64_t h1 = finish_t<KIND>(decade_state_t<KIND>(cs[owner * 3 + 0], K.s1, x), K.s1, y);
+            const uint64_t h2 = finish_t<KIND>(decade_state_t<KIND>(cs[owner * 3 + 1], K.s2, x), K.s2, y);
+            uint32_t idx = mod_u64(h1, K.fm);
+            const uint32_t step = mod_u64(h2, K.fm);
+            for (uint32_t p = 0; p < K.fk; p++) {
+                red_or_global(bits + (idx >> 5), 1u << (idx & 31u));
+                idx = addmod(idx, step, K.fm.m);
+            }
+            if (K.has_act) {
+                const uint64_t hA = finish_t<KIND>(decade_state_t<KIND>(cs[owner * 3 + 2], K.sA, x), K.sA, y);
+                if (hA < K.T) red_or_global(bits + (idx >> 5), 1u << (idx & 31u));
+            }
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(I2_WARPS * 32) k_insert2(const FrameJob* __restrict__ jobs) {
+    const FrameJob& J = jobs[blockIdx.y];
+    if (J.l == 0) return;
+    __shared__ uint64_t s_cs[I2_WARPS][32 * 3];
+    __shared__ uint16_t s_list[I2_WARPS][I2_LIST];
+    const FilterK K = filter_consts(J);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t ncent = (J.n + 99u) / 100u;
+    const uint32_t nslab = (ncent + 31u) / 32u;
+    for (uint32_t sl = blockIdx.x * I2_WARPS + warp; sl < nslab; sl += gridDim.x * I2_WARPS) {
+        const uint32_t slab = sl * 32u, c = slab + lane;
+        const bool active = c < ncent;
+        Bits128 mb; mb.lo = 0; mb.hi = 0;
+        if (active) mb = load_bits100(J.mask, c, min(100u, J.n - 100u * c));
+        if (!__any_sync(0xffffffffu, (mb.lo | mb.hi) != 0ull)) continue;
+        const uint32_t last = min(slab + 31u, ncent - 1u);
+        const bool uniform = slab >= 1u && ndigits_u32(slab) == ndigits_u32(last);
+        if (uniform) {
+            const Century cen = make_century(active ? c : slab);
+            switch (cen.kind) {
+            case K_4B: insert_slab_dense<K_4B>(K, J.bits, mb, cen, s_cs[warp], s_list[warp], lane); break;
+            case K_8B: insert_slab_dense<K_8B>(K, J.bits, mb, cen, s_cs[warp], s_list[warp], lane); break;
+            case K_44: insert_slab_dense<K_44>(K, J.bits, mb, cen, s_cs[warp], s_list[warp], lane); break;
+            case K_88: insert_slab_dense<K_88>(K, J.bits, mb, cen, s_cs[warp], s_list[warp], lane); break;
+            default:   insert_slab_dense<K_BB>(K, J.bits, mb, cen, s_cs[warp], s_list[warp], lane); break;
+            }
+        } else if ((mb.lo | mb.hi) != 0ull) {             // century 0 or a digit-count boundary: per-lane form
+            const Century cen = make_century(c);
+            const uint64_t C1 = century_state(cen, K.s1), C2 = century_state(cen, K.s2), CA = century_state(cen, K.sA);
+            for (int half = 0; half < 2; half++) {
+                uint64_t v = half ? mb.hi : mb.lo;
+                while (v) {
+                    const uint32_t pos = (uint32_t)(__ffsll((long long)v) - 1) + 64u * half;
+                    v &= v - 1ull;
+                    const uint32_t x = pos / 10u, y = pos - 10u * x;
+                    insert_hashes(J.bits, K, finish(cen.kind, decade_state(cen, C1, K.s1, x), K.s1, y),
+                                  finish(cen.kind, decade_state(cen, C2, K.s2, x), K.s2, y),
+                                  K.has_act ? finish(cen.kind, decade_state(cen, CA, K.sA, x), K.sA, y) : 0ull);
+                }
             }
         }
     }
@@ -873,8 +975,8 @@ __global__ void __launch_bounds__(1024) k_witness(const FrameJob* __restrict__ j
         if (cnt) or_bits128(J.witness, (uint64_t)base + off, wlo, whi);
         base += tot;
     }
+    __threadfence();                                    // the RED.ORs above must be performed before the in-place pass below
     __syncthreads();
-    __threadfence_block();
     const uint32_t wwords = (base + 31u) >> 5;
     for (uint32_t i = threadIdx.x; i < wwords; i += blockDim.x) J.witness[i] = bitrev_bytes(__ldcg(J.witness + i));
     const uint32_t bwords = (J.l + 31u) >> 5;
@@ -1098,8 +1200,17 @@ cudaError_t launch_threshold(const PairJob* d_pairs, int F, uint32_t npix, int c
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_insert(const FrameJob* d_jobs, int F, uint32_t max_centuries, int sm_count, cudaStream_t st) {
+cudaError_t launch_insert(const FrameJob* d_jobs, int F, uint32_t max_centuries, int variant, int sm_count, cudaStream_t st) {
     if (F <= 0 || max_centuries == 0) return cudaSuccess;
+    if (variant == 1) {                                   // dense, warp-compacted insert
+        const uint32_t nslab = (max_centuries + 31u) / 32u;
+        uint32_t bx = (nslab + I2_WARPS - 1) / I2_WARPS;
+        const uint32_t cap = (uint32_t)(sm_count * 12);
+        if ((uint64_t)bx * (uint64_t)F > cap) { bx = (cap + (uint32_t)F - 1u) / (uint32_t)F; if (bx < 1u) bx = 1u; }
+        dim3 grid(bx, (unsigned)F);
+        k_insert2<<<grid, I2_WARPS * 32, 0, st>>>(d_jobs);
+        return cudaGetLastError();
+    }
     uint32_t bx = (max_centuries + 255u) / 256u;
     const uint32_t cap = (uint32_t)(sm_count * 16);
     if ((uint64_t)bx * (uint64_t)F > cap) { bx = (cap + (uint32_t)F - 1u) / (uint32_t)F; if (bx < 1u) bx = 1u; }
@@ -1107,6 +1218,7 @@ cudaError_t launch_insert(const FrameJob* d_jobs, int F, uint32_t max_centuries,
     k_insert<<<grid, 256, 0, st>>>(d_jobs);
     return cudaGetLastError();
 }
+
 
 int query_max_smem_bytes() { return 232448 - 1024; }    // 227 KB opt-in minus static shared memory + slack
 
