@@ -682,15 +682,25 @@ __device__ __forceinline__ void red_or_shared_if(uint32_t addr, uint32_t v, bool
     asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q red.shared.or.b32 [%0], %1;\n}" ::"r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
 }
 
-// bit `idx` of the Bloom array: words [0, sm_words) from shared memory, the rest through L2 (read-only path)
-template <bool HYBRID>
-__device__ __forceinline__ uint32_t probe_bit(uint32_t sm_addr, const uint32_t* __restrict__ gl, uint32_t sm_words, uint32_t idx) {
+// bit `idx` of the Bloom array.  PM (probe mode):
+//   0  the whole array is in this CTA's shared memory
+//   1  words [0, sm_words) in shared memory, the rest through L2 (read-only path)
+//   2  the array is split over the shared memories of a 2-CTA cluster (DSMEM): words [0, sm_words) live in
+//      rank 0 (cluster address sm_addr), the rest in rank 1 (sm_addr1 is pre-biased by -4*sm_words)
+template <int PM>
+__device__ __forceinline__ uint32_t probe_bit(uint32_t sm_addr, uint32_t sm_addr1, const uint32_t* __restrict__ gl,
+                                              uint32_t sm_words, uint32_t idx) {
     const uint32_t w = idx >> 5;
     uint32_t word;
-    if (HYBRID) {
+    if (PM == 1) {
         asm("{\n .reg .pred q;\n setp.lt.u32 q, %1, %2;\n @q ld.shared.u32 %0, [%3];\n @!q ld.global.nc.u32 %0, [%4];\n}"
             : "=r"(word)
             : "r"(w), "r"(sm_words), "r"(sm_addr + 4u * w), "l"(gl + w));
+    } else if (PM == 2) {
+        asm("{\n .reg .pred q;\n .reg .u32 b;\n setp.lt.u32 q, %1, %2;\n selp.u32 b, %3, %4, q;\n mad.lo.u32 b, %1, 4, b;\n"
+            " ld.shared::cluster.u32 %0, [b];\n}"
+            : "=r"(word)
+            : "r"(w), "r"(sm_words), "r"(sm_addr), "r"(sm_addr1));
     } else {
         asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(sm_addr + 4u * w));
     }
@@ -721,8 +731,8 @@ struct RingState {                 // warp-uniform
 };
 
 // stage B (32 survivors of A) and stage C (32 survivors of B); `force` drains partial batches
-template <int KIND, int FKT, bool HYBRID>
-__device__ __forceinline__ void drain_stages(const FilterK& K, uint32_t sm_addr, const uint32_t* __restrict__ gl,
+template <int KIND, int FKT, int PM>
+__device__ __forceinline__ void drain_stages(const FilterK& K, uint32_t sm_addr, uint32_t sm_addr1, const uint32_t* __restrict__ gl,
                                              uint32_t sm_words, uint32_t qb_addr, uint32_t qc_addr, uint32_t pacc_addr,
                                              uint32_t lane, uint32_t lt, uint64_t CA, RingState& R, bool force) {
     if (R.qb_cnt >= 32u || (force && R.qb_cnt > 0u)) {               // ---- stage B
@@ -739,12 +749,12 @@ __device__ __forceinline__ void drain_stages(const FilterK& K, uint32_t sm_addr,
 #pragma unroll
             for (int i = 1; i < FKT; i++) {
                 idx = addmod_fast(idx, stepm, K.fm.m);
-                ok &= probe_bit<HYBRID>(sm_addr, gl, sm_words, idx);
+                ok &= probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx);
             }
         } else {
             for (uint32_t i = 1; i < K.fk; i++) {
                 idx = addmod_fast(idx, stepm, K.fm.m);
-                ok &= probe_bit<HYBRID>(sm_addr, gl, sm_words, idx);
+                ok &= probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx);
                 if (!__any_sync(0xffffffffu, ok != 0u)) break;
             }
         }
@@ -769,13 +779,13 @@ __device__ __forceinline__ void drain_stages(const FilterK& K, uint32_t sm_addr,
         const uint64_t CAo = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)CA, owner) |
                              ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(CA >> 32), owner) << 32);
         const uint64_t hA = finish_t<KIND>(decade_state_t<KIND>(CAo, K.sA, (tag >> 4) & 15u), K.sA, tag & 15u);
-        const uint32_t pb = probe_bit<HYBRID>(sm_addr, gl, sm_words, have ? r.x : 0u);
+        const uint32_t pb = probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, have ? r.x : 0u);
         deliver_pass(pacc_addr, tag, have && (!(hA < K.T) || pb != 0u));
     }
 }
 
-template <int KIND, int FKT, bool HYBRID>
-__device__ __noinline__ void query_slab_staged(const FilterK K, uint32_t sm_addr, const uint32_t* __restrict__ gl,
+template <int KIND, int FKT, int PM>
+__device__ __noinline__ void query_slab_staged(const FilterK K, uint32_t sm_addr, uint32_t sm_addr1, const uint32_t* __restrict__ gl,
                                                uint32_t sm_words, const uint32_t* __restrict__ mask, uint32_t n,
                                                uint32_t slab_c0, uint32_t c_end, uint4* __restrict__ pass4,
                                                uint32_t qb_addr, uint32_t qc_addr, uint32_t pacc_addr) {
@@ -805,8 +815,8 @@ __device__ __noinline__ void query_slab_staged(const FilterK K, uint32_t sm_addr
         for (uint32_t y = 0; y < 10u; y += 2u) {                     // ---- stage A: two positions per lane (ILP)
             const uint32_t idxA = mod_fast(finish_t<KIND>(D1, K.s1, y), K.fm);
             const uint32_t idxB = mod_fast(finish_t<KIND>(D1, K.s1, y + 1u), K.fm);
-            const uint32_t bA = probe_bit<HYBRID>(sm_addr, gl, sm_words, idxA);
-            const uint32_t bB = probe_bit<HYBRID>(sm_addr, gl, sm_words, idxB);
+            const uint32_t bA = probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idxA);
+            const uint32_t bB = probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idxB);
             const bool svA = (bA & ~(skip10 >> y) & 1u) != 0u;
             const bool svB = (bB & ~(skip10 >> (y + 1u)) & 1u) != 0u;
 #pragma unroll 1
@@ -816,13 +826,13 @@ __device__ __noinline__ void query_slab_staged(const FilterK K, uint32_t sm_addr
                 sts128_if(qb_addr + 16u * ((R.qb_head + R.qb_cnt + __popc(b & lt)) & (Q2_RING - 1)), j ? idxB : idxA,
                           tagx | (y + j), (uint32_t)D2, (uint32_t)(D2 >> 32), sv);
                 R.qb_cnt += __popc(b);
-                drain_stages<KIND, FKT, HYBRID>(K, sm_addr, gl, sm_words, qb_addr, qc_addr, pacc_addr, lane, lt, CA, R, false);
+                drain_stages<KIND, FKT, PM>(K, sm_addr, sm_addr1, gl, sm_words, qb_addr, qc_addr, pacc_addr, lane, lt, CA, R, false);
             }
         }
     }
 #pragma unroll 1
     while (R.qb_cnt | R.qc_cnt)                                      // end of the slab: drain what is left
-        drain_stages<KIND, FKT, HYBRID>(K, sm_addr, gl, sm_words, qb_addr, qc_addr, pacc_addr, lane, lt, CA, R, true);
+        drain_stages<KIND, FKT, PM>(K, sm_addr, sm_addr1, gl, sm_words, qb_addr, qc_addr, pacc_addr, lane, lt, CA, R, true);
     __syncwarp();
     uint4 acc = lds128(pacc_addr + 16u * lane);
     sts128_if(pacc_addr + 16u * lane, 0u, 0u, 0u, 0u, true);
@@ -833,17 +843,117 @@ __device__ __noinline__ void query_slab_staged(const FilterK K, uint32_t sm_addr
     __syncwarp();
 }
 
-template <int KIND, bool HYBRID>
-__device__ __forceinline__ void query_slab_dispatch(const FilterK& K, uint32_t sm_addr, const uint32_t* __restrict__ gl,
+// ------------------------------------------------------------------------------------------
+// K3 (dense A+B): stage B's hash is computed speculatively for EVERY position next to stage A's
+// (two independent XXH64 chains per position -> ILP, and no A->B ring: at a ~50 % survival rate the
+// ring bookkeeping costs more issue slots than the wasted half of the h2 hashes).  Only the ~12 % of
+// positions that pass all deterministic probes are compacted into the stage-C ring.
+// ------------------------------------------------------------------------------------------
+template <int KIND, int FKT, int PM>
+__device__ __noinline__ void query_slab_dense(const FilterK K, uint32_t sm_addr, uint32_t sm_addr1,
+                                              const uint32_t* __restrict__ gl, uint32_t sm_words,
+                                              const uint32_t* __restrict__ mask, uint32_t n, uint32_t slab_c0,
+                                              uint32_t c_end, uint4* __restrict__ pass4, uint32_t qc_addr,
+                                              uint32_t pacc_addr) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t c = slab_c0 + lane;
+    const bool active = c < c_end;
+    const Century cen = make_century(active ? c : slab_c0);
+    const uint64_t C1 = century_state(cen, K.s1), C2 = century_state(cen, K.s2), CA = century_state(cen, K.sA);
+    const uint32_t nvalid = active ? min(100u, n - 100u * c) : 0u;
+    Bits128 mb; mb.lo = 0; mb.hi = 0;
+    if (active && mask != nullptr) mb = load_bits100(mask, c, nvalid);
+    uint64_t skip_lo = mb.lo, skip_hi = mb.hi;                       // known members and positions beyond n
+    if (nvalid < 64u) { skip_hi = ~0ull; skip_lo |= ~((1ull << nvalid) - 1ull); }
+    else skip_hi |= ~((1ull << (nvalid - 64u)) - 1ull);
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t qc_head = 0, qc_cnt = 0;
+#pragma unroll 1
+    for (uint32_t x = 0; x <= 10u; x++) {                            // x == 10: drain what is left in ring C
+        const bool feeding = x < 10u;
+        uint64_t D1 = 0, D2 = 0;
+        uint32_t skip10 = 0x3ffu;
+        if (feeding) {
+            D1 = decade_state_t<KIND>(C1, K.s1, x);
+            D2 = decade_state_t<KIND>(C2, K.s2, x);
+            const uint32_t p0 = 10u * x;
+            const uint64_t sh = (p0 < 64u) ? ((skip_lo >> p0) | (p0 ? (skip_hi << (64u - p0)) : 0ull)) : (skip_hi >> (p0 - 64u));
+            skip10 = (uint32_t)sh & 0x3ffu;
+        }
+        const uint32_t tagx = (lane << 8) | (x << 4);
+#pragma unroll 1
+        for (uint32_t y = 0; y < 10u; y++) {
+            if (feeding) {                                           // ---- stages A + B, every position
+                const uint32_t idx0 = mod_fast(finish_t<KIND>(D1, K.s1, y), K.fm);
+                const uint32_t stepm = mod_fast(finish_t<KIND>(D2, K.s2, y), K.fm);
+                uint32_t ok = probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx0) & ~(skip10 >> y) & 1u;
+                uint32_t idx = idx0;
+                if (FKT > 0) {
+#pragma unroll
+                    for (int i = 1; i < FKT; i++) {
+                        idx = addmod_fast(idx, stepm, K.fm.m);
+                        ok &= probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx);
+                    }
+                } else {
+                    for (uint32_t i = 1; i < K.fk; i++) {
+                        idx = addmod_fast(idx, stepm, K.fm.m);
+                        ok &= probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx);
+                    }
+                }
+                if (K.has_act) {
+                    idx = addmod_fast(idx, stepm, K.fm.m);           // index of probe floor_k
+                    const uint32_t b2 = __ballot_sync(0xffffffffu, ok != 0u);
+                    sts64_if(qc_addr + 8u * ((qc_head + qc_cnt + __popc(b2 & lt)) & (Q2_RING - 1)), idx, tagx | y, ok != 0u);
+                    qc_cnt += __popc(b2);
+                } else {
+                    deliver_pass(pacc_addr, tagx | y, ok != 0u);
+                }
+            }
+            if (qc_cnt >= 32u || (!feeding && qc_cnt > 0u)) {        // ---- stage C: 32 survivors
+                __syncwarp();
+                const uint32_t nc = min(32u, qc_cnt);
+                const bool have = lane < nc;
+                const uint2 r = lds64(qc_addr + 8u * ((qc_head + lane) & (Q2_RING - 1)));
+                qc_head = (qc_head + nc) & (Q2_RING - 1);
+                qc_cnt -= nc;
+                const uint32_t tag = have ? r.y : 0u;
+                const uint32_t owner = tag >> 8;
+                const uint64_t CAo = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)CA, owner) |
+                                     ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(CA >> 32), owner) << 32);
+                const uint64_t hA = finish_t<KIND>(decade_state_t<KIND>(CAo, K.sA, (tag >> 4) & 15u), K.sA, tag & 15u);
+                const uint32_t pb = probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, have ? r.x : 0u);
+                deliver_pass(pacc_addr, tag, have && (!(hA < K.T) || pb != 0u));
+            }
+            if (!feeding && qc_cnt == 0u) break;
+        }
+    }
+    __syncwarp();
+    uint4 acc = lds128(pacc_addr + 16u * lane);
+    sts128_if(pacc_addr + 16u * lane, 0u, 0u, 0u, 0u, true);
+    if (active) {
+        acc.x |= (uint32_t)mb.lo; acc.y |= (uint32_t)(mb.lo >> 32); acc.z |= (uint32_t)mb.hi; acc.w |= (uint32_t)(mb.hi >> 32);
+        pass4[c] = acc;
+    }
+    __syncwarp();
+}
+
+template <int KIND, int PM, int ALG = 0>
+__device__ __forceinline__ void query_slab_dispatch(const FilterK& K, uint32_t sm_addr, uint32_t sm_addr1, const uint32_t* __restrict__ gl,
                                                     uint32_t sm_words, const uint32_t* __restrict__ mask, uint32_t n,
                                                     uint32_t slab_c0, uint32_t c_end, uint4* __restrict__ pass4, uint32_t qb,
                                                     uint32_t qc, uint32_t pacc) {
-    if (K.fk == 3u) query_slab_staged<KIND, 3, HYBRID>(K, sm_addr, gl, sm_words, mask, n, slab_c0, c_end, pass4, qb, qc, pacc);
-    else if (K.fk == 2u) query_slab_staged<KIND, 2, HYBRID>(K, sm_addr, gl, sm_words, mask, n, slab_c0, c_end, pass4, qb, qc, pacc);
-    else query_slab_staged<KIND, 0, HYBRID>(K, sm_addr, gl, sm_words, mask, n, slab_c0, c_end, pass4, qb, qc, pacc);
+    if (ALG == 1) {                                       // dense A+B, ring only before stage C
+        if (K.fk == 3u) query_slab_dense<KIND, 3, PM>(K, sm_addr, sm_addr1, gl, sm_words, mask, n, slab_c0, c_end, pass4, qc, pacc);
+        else if (K.fk == 2u) query_slab_dense<KIND, 2, PM>(K, sm_addr, sm_addr1, gl, sm_words, mask, n, slab_c0, c_end, pass4, qc, pacc);
+        else query_slab_dense<KIND, 0, PM>(K, sm_addr, sm_addr1, gl, sm_words, mask, n, slab_c0, c_end, pass4, qc, pacc);
+    } else {
+        if (K.fk == 3u) query_slab_staged<KIND, 3, PM>(K, sm_addr, sm_addr1, gl, sm_words, mask, n, slab_c0, c_end, pass4, qb, qc, pacc);
+        else if (K.fk == 2u) query_slab_staged<KIND, 2, PM>(K, sm_addr, sm_addr1, gl, sm_words, mask, n, slab_c0, c_end, pass4, qb, qc, pacc);
+        else query_slab_staged<KIND, 0, PM>(K, sm_addr, sm_addr1, gl, sm_words, mask, n, slab_c0, c_end, pass4, qb, qc, pacc);
+    }
 }
 
-template <bool HYBRID>
+template <bool HYBRID, int ALG>
 __global__ void __launch_bounds__(Q2_THREADS, 1) k_query2(const FrameJob* __restrict__ jobs,
                                                           const uint32_t* __restrict__ cent_prefix, int F,
                                                           uint32_t smem_words_cap) {
@@ -888,11 +998,11 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_query2(const FrameJob* __rest
             const bool uniform = slab >= 1u && ndigits_u32(slab) == ndigits_u32(last) && K.fk >= 1u && K.fm.fast;
             if (uniform) {
                 switch (make_century(slab).kind) {
-                case K_4B: query_slab_dispatch<K_4B, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                case K_8B: query_slab_dispatch<K_8B, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                case K_44: query_slab_dispatch<K_44, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                case K_88: query_slab_dispatch<K_88, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                default:   query_slab_dispatch<K_BB, HYBRID>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_4B: query_slab_dispatch<K_4B, (HYBRID ? 1 : 0), ALG>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_8B: query_slab_dispatch<K_8B, (HYBRID ? 1 : 0), ALG>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_44: query_slab_dispatch<K_44, (HYBRID ? 1 : 0), ALG>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_88: query_slab_dispatch<K_88, (HYBRID ? 1 : 0), ALG>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                default:   query_slab_dispatch<K_BB, (HYBRID ? 1 : 0), ALG>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
                 }
             } else {                                    // century 0, a digit-count boundary, or floor_k == 0
                 const uint32_t c = slab + lane;
@@ -905,6 +1015,89 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_query2(const FrameJob* __rest
         }
         g = seg_end;
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 (cluster): the same staged query for Bloom arrays that do not fit one CTA's shared memory.
+// A cluster of two CTAs (two SMs) shares one frame: each CTA stages HALF of the bit array with TMA
+// into its own shared memory and probes the other half through distributed shared memory
+// (ld.shared::cluster), so no probe goes to L2.  The two CTAs interleave the slabs of the cluster's
+// century range; two cluster barriers per frame segment order the re-staging.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q2_THREADS, 1)
+k_query2c(const FrameJob* __restrict__ jobs, const uint32_t* __restrict__ cent_prefix, int F, uint32_t half_words_cap) {
+    extern __shared__ __align__(128) uint32_t dyn[];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+    uint32_t* wq = dyn + warp * Q2_WARP_WORDS;
+    const uint32_t qb = smem_u32(wq), qc = smem_u32(wq + Q2_RING * 4), pacc = smem_u32(wq + Q2_RING * 4 + Q2_RING * 2);
+    uint32_t* sbits = dyn + Q2_WARPS * Q2_WARP_WORDS;
+    const uint32_t base0 = mapa_shared(smem_u32(sbits), 0u), base1 = mapa_shared(smem_u32(sbits), 1u);
+    sts128_if(pacc + 16u * lane, 0u, 0u, 0u, 0u, true);
+    const uint32_t total = cent_prefix[F];
+    const uint32_t lo = (uint32_t)(((uint64_t)total * cid) / ncl);
+    const uint32_t hi = (uint32_t)(((uint64_t)total * (cid + 1)) / ncl);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    int f = 0;
+    { int a = 0, b = F; while (a < b) { int m = (a + b) >> 1; if (cent_prefix[m + 1] > lo) b = m; else a = m + 1; } f = a; }
+    uint32_t parity = 0, g = lo;
+    while (g < hi) {                                                  // both CTAs of the cluster walk the same segments
+        while (cent_prefix[f + 1] <= g) f++;
+        const FrameJob& J = jobs[f];
+        const uint32_t seg_end = min(hi, cent_prefix[f + 1]);
+        const uint32_t c_begin = g - cent_prefix[f], c_end = seg_end - cent_prefix[f];
+        const uint32_t nwords = ((J.l + 31u) >> 5);
+        const uint32_t hw = min(((((nwords + 1u) >> 1) + 3u) & ~3u), half_words_cap);   // words held by rank 0
+        const uint32_t mine_begin = rank ? hw : 0u;
+        const uint32_t mine_words = rank ? ((nwords > hw ? nwords - hw : 0u) + 3u) & ~3u : hw;
+        cluster_sync_all();                                           // nobody still probes the previous array
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&bar, mine_words * 4u);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(J.bits + mine_begin);
+            uint8_t* dst = reinterpret_cast<uint8_t*>(sbits);
+            for (uint32_t off = 0; off < mine_words * 4u; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, mine_words * 4u - off), &bar);
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+        cluster_sync_all();                                           // both halves are in place
+        const FilterK K = filter_consts(J);
+        uint4* pass4 = reinterpret_cast<uint4*>(J.pass);
+        const uint32_t a1 = base1 - 4u * hw;
+        for (uint32_t slab = c_begin + 32u * (warp + Q2_WARPS * rank); slab < c_end; slab += 64u * Q2_WARPS) {
+            const uint32_t last = min(slab + 31u, c_end - 1u);
+            const bool uniform = slab >= 1u && ndigits_u32(slab) == ndigits_u32(last) && K.fk >= 1u && K.fm.fast;
+            if (uniform) {
+                switch (make_century(slab).kind) {
+                case K_4B: query_slab_dispatch<K_4B, 2>(K, base0, a1, J.bits, hw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_8B: query_slab_dispatch<K_8B, 2>(K, base0, a1, J.bits, hw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_44: query_slab_dispatch<K_44, 2>(K, base0, a1, J.bits, hw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_88: query_slab_dispatch<K_88, 2>(K, base0, a1, J.bits, hw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                default:   query_slab_dispatch<K_BB, 2>(K, base0, a1, J.bits, hw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                }
+            } else {                                    // rare slabs: probe the global copy
+                const uint32_t c = slab + lane;
+                if (c < c_end) {
+                    BitView bv; bv.sm = sbits; bv.gl = J.bits; bv.sm_words = 0u;
+                    const Bits128 r = query_century(bv, K, c, min(100u, J.n - 100u * c));
+                    pass4[c] = make_uint4((uint32_t)r.lo, (uint32_t)(r.lo >> 32), (uint32_t)r.hi, (uint32_t)(r.hi >> 32));
+                }
+            }
+        }
+        g = seg_end;
+    }
+    cluster_sync_all();                                               // a peer may still be reading this CTA's half
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1222,16 +1415,16 @@ cudaError_t launch_insert(const FrameJob* d_jobs, int F, uint32_t max_centuries,
 
 int query_max_smem_bytes() { return 232448 - 1024; }    // 227 KB opt-in minus static shared memory + slack
 
-template <bool HYBRID>
+template <bool HYBRID, int ALG>
 static cudaError_t launch_query2_t(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, int F, uint32_t total_centuries,
                                    int sm_count, int smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(k_query2<HYBRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_query2<HYBRID, ALG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     uint32_t grid = (uint32_t)sm_count;
     const uint32_t max_useful = (total_centuries + Q2_THREADS - 1) / Q2_THREADS;
     if (grid > max_useful) grid = max_useful;
     if (grid < 1u) grid = 1u;
-    k_query2<HYBRID><<<grid, Q2_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F,
+    k_query2<HYBRID, ALG><<<grid, Q2_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F,
                                                      (uint32_t)((smem - Q2_WARPS * Q2_WARP_WORDS * 4) / 4));
     return cudaGetLastError();
 }
@@ -1242,14 +1435,30 @@ cudaError_t launch_query(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, 
     int cap = smem_bytes_cap & ~15;
     if (cap > query_max_smem_bytes()) cap = query_max_smem_bytes() & ~15;
     const uint32_t need_words = (((max_l_bits + 31u) >> 5) + 3u) & ~3u;
-    if (variant == 1) {                                   // staged, queue-compacted kernel
+    if (variant >= 1) {                                   // staged, queue-compacted kernels
         const int qbytes = Q2_WARPS * Q2_WARP_WORDS * 4;
         if (cap < qbytes + 1024) cap = qbytes + 1024;
         const int bits_cap = cap - qbytes;
-        const bool hybrid = (size_t)need_words * 4 > (size_t)bits_cap;
-        const int smem = qbytes + (hybrid ? bits_cap : (int)(need_words * 4 < 16 ? 16 : need_words * 4));
-        return hybrid ? launch_query2_t<true>(d_jobs, d_cent_prefix, F, total_centuries, sm_count, smem, st)
-                      : launch_query2_t<false>(d_jobs, d_cent_prefix, F, total_centuries, sm_count, smem, st);
+        const bool fits = (size_t)need_words * 4 <= (size_t)bits_cap;
+        const uint32_t half_words = ((((need_words + 1u) >> 1) + 3u) & ~3u) + 4u;
+        if (variant == 2 && !fits && (size_t)half_words * 4 <= (size_t)bits_cap && sm_count >= 2) {
+            // two-CTA clusters: each CTA holds half of the array, the other half is probed through DSMEM
+            const int smem = qbytes + (int)(half_words * 4);
+            cudaError_t e = cudaFuncSetAttribute(k_query2c, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            uint32_t grid = (uint32_t)(sm_count & ~1);
+            const uint32_t max_useful = 2u * ((total_centuries + 2 * Q2_THREADS - 1) / (2 * Q2_THREADS));
+            if (grid > max_useful) grid = max_useful;
+            if (grid < 2u) grid = 2u;
+            k_query2c<<<grid, Q2_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F, (uint32_t)((smem - qbytes) / 4));
+            return cudaGetLastError();
+        }
+        const int smem = qbytes + (fits ? (int)(need_words * 4 < 16 ? 16 : need_words * 4) : bits_cap);
+        if (variant == 3)
+            return !fits ? launch_query2_t<true, 1>(d_jobs, d_cent_prefix, F, total_centuries, sm_count, smem, st)
+                         : launch_query2_t<false, 1>(d_jobs, d_cent_prefix, F, total_centuries, sm_count, smem, st);
+        return !fits ? launch_query2_t<true, 0>(d_jobs, d_cent_prefix, F, total_centuries, sm_count, smem, st)
+                     : launch_query2_t<false, 0>(d_jobs, d_cent_prefix, F, total_centuries, sm_count, smem, st);
     }
     int smem = (size_t)need_words * 4 > (size_t)cap ? cap : (int)(need_words * 4);
     if (smem < 16) smem = 16;
