@@ -160,6 +160,19 @@ int rbf_stream_bitmap_region(rbf_stream* s, void** dptr, uint64_t* stride_bytes)
  * out = { K1 threshold, host round trip + job upload + memsets, K2 insert, K3 query, K3b witness } in ms */
 int rbf_stream_stage_ms(rbf_stream* s, double out[5]);
 
+/* ---- SURVEY 8(f) rows N1 / N2, device side
+ * N1  changed-value gather of VideoFrameCompressor._calculate_frame_diff (ivc:810-842): for each pair of the last
+ *     encode, the interleaved channel values (native sample type) of the CURRENT frame at the mask's set positions, in
+ *     row-major order.  offsets_out[pairs+1] = byte offsets per pair; values_out == NULL only fills the offsets. */
+int rbf_stream_gather_changed(rbf_stream* s, uint32_t pairs, uint8_t* values_out, uint64_t values_capacity,
+                              uint64_t* offsets_out);
+/* N2  VideoFrameCompressor._apply_frame_diff (ivc:849-909): store[out_frame] = store[base_frame] with the pixels selected
+ *     by the mask (n bits, little bit order) replaced by `values` in rank order; when the value count does not match the
+ *     mask the base frame is copied unchanged (ivc:882) and *applied_pixels = 0. */
+int rbf_stream_apply_diff(rbf_stream* s, uint32_t base_frame, uint32_t out_frame, const uint8_t* mask_packed_little,
+                          const uint8_t* values, uint64_t values_bytes, uint64_t* applied_pixels);
+int rbf_stream_download(rbf_stream* s, uint32_t frame, void* host_out);
+
 /* ------------------------------------------------------------------ multi-GPU (one process per GPU)
  * frames are sharded across ranks; the per-rank Bloom bit arrays are exchanged with ONE ncclAllGather
  * over NVLink.  NCCL is dlopen'ed (libnccl.so.2); the unique id travels over the caller's own channel. */

@@ -804,6 +804,88 @@ extern "C" int rbf_stream_decode_verify(rbf_stream* s, uint32_t pairs, uint64_t*
     return RBF_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// N1 / N2: changed-value gather and frame reconstruction on the device
+// ------------------------------------------------------------------------------------------
+extern "C" int rbf_stream_gather_changed(rbf_stream* s, uint32_t pairs, uint8_t* values_out, uint64_t capacity,
+                                         uint64_t* offsets_out) {
+    if (!s || !offsets_out) return set_err(s ? s->c : nullptr, RBF_ERR_INVALID, "rbf_stream_gather_changed: NULL");
+    rbf_ctx* c = s->c;
+    if (pairs == 0 || pairs > s->last_pairs) return set_err(c, RBF_ERR_INVALID, "only %u pairs were encoded", s->last_pairs);
+    CK(c, cudaSetDevice(c->device));
+    const uint64_t pb = (uint64_t)s->C * s->S;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < pairs; i++) { offsets_out[i] = total; total += s->last_infos[i].ones * pb; }
+    offsets_out[pairs] = total;
+    if (!values_out) return RBF_OK;                      // size query
+    if (capacity < total) return set_err(c, RBF_ERR_INVALID, "values buffer too small: %llu < %llu", (unsigned long long)capacity, (unsigned long long)total);
+    void *d_vals, *d_jobs;
+    int rc;
+    if ((rc = scratch_get(c, 8, (size_t)total + 256, &d_vals)) || (rc = scratch_get(c, 9, sizeof(GatherJob) * pairs, &d_jobs))) return rc;
+    std::vector<GatherJob> jobs(pairs);
+    for (uint32_t i = 0; i < pairs; i++) {
+        jobs[i].mask = s->d_mask + (size_t)i * s->mask_stride_w;
+        jobs[i].frame = s->h_pairs[i].curr;
+        jobs[i].values = (uint8_t*)d_vals + offsets_out[i];
+        jobs[i].out_frame = nullptr;
+        jobs[i].npix = (uint32_t)s->npix;
+        jobs[i].pix_bytes = (uint32_t)pb;
+    }
+    CK(c, cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(GatherJob) * pairs, cudaMemcpyHostToDevice, c->st));
+    LAUNCH(c, launch_gather_scatter((const GatherJob*)d_jobs, (int)pairs, 0, nullptr, c->st));
+    if (total) { CK(c, cudaMemcpyAsync(values_out, d_vals, (size_t)total, cudaMemcpyDeviceToHost, c->st)); c->d2h += (int64_t)total; }
+    CK(c, cudaStreamSynchronize(c->st));
+    return RBF_OK;
+}
+
+extern "C" int rbf_stream_apply_diff(rbf_stream* s, uint32_t base_frame, uint32_t out_frame, const uint8_t* mask_packed_little,
+                                     const uint8_t* values, uint64_t values_bytes, uint64_t* applied_pixels) {
+    if (!s || !mask_packed_little || (!values && values_bytes)) return set_err(s ? s->c : nullptr, RBF_ERR_INVALID, "rbf_stream_apply_diff: NULL");
+    rbf_ctx* c = s->c;
+    if (base_frame >= s->max_frames || out_frame >= s->max_frames) return set_err(c, RBF_ERR_INVALID, "frame index outside the store");
+    CK(c, cudaSetDevice(c->device));
+    const uint64_t pb = (uint64_t)s->C * s->S;
+    const size_t mbytes = (size_t)((s->npix + 7) / 8), mwords = s->mask_stride_w;
+    void *d_mask, *d_vals, *d_job;
+    int rc;
+    if ((rc = scratch_get(c, 10, mwords * 4, &d_mask)) || (rc = scratch_get(c, 8, (size_t)values_bytes + 256, &d_vals)) ||
+        (rc = scratch_get(c, 9, sizeof(GatherJob) + 64, &d_job)))
+        return rc;
+    CK(c, cudaMemsetAsync(d_mask, 0, mwords * 4, c->st));
+    CK(c, cudaMemcpyAsync(d_mask, mask_packed_little, mbytes, cudaMemcpyHostToDevice, c->st)); c->h2d += (int64_t)mbytes;
+    if (values_bytes) { CK(c, cudaMemcpyAsync(d_vals, values, (size_t)values_bytes, cudaMemcpyHostToDevice, c->st)); c->h2d += (int64_t)values_bytes; }
+    uint8_t* dst = s->d_frames + (size_t)out_frame * s->frame_stride;
+    if (out_frame != base_frame)
+        CK(c, cudaMemcpyAsync(dst, s->d_frames + (size_t)base_frame * s->frame_stride, s->frame_bytes, cudaMemcpyDeviceToDevice, c->st));
+    GatherJob J;
+    J.mask = (const uint32_t*)d_mask; J.frame = nullptr; J.values = (uint8_t*)d_vals; J.out_frame = dst;
+    J.npix = (uint32_t)s->npix; J.pix_bytes = (uint32_t)pb;
+    uint32_t* d_cnt = (uint32_t*)((uint8_t*)d_job + sizeof(GatherJob));
+    // the reference applies the diff only when the value count matches the mask (ivc:882): count first
+    CK(c, cudaMemsetAsync(d_cnt, 0, 4, c->st));
+    LAUNCH(c, launch_popcount((const uint32_t*)d_mask, (s->npix + 31) / 32, d_cnt, c->st));
+    uint32_t h_cnt = 0;
+    CK(c, cudaMemcpyAsync(&h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+    if (applied_pixels) *applied_pixels = 0;
+    if ((uint64_t)h_cnt * pb != values_bytes) return RBF_OK;       // ivc:882: mismatch -> the base frame is returned unchanged
+    CK(c, cudaMemcpyAsync(d_job, &J, sizeof J, cudaMemcpyHostToDevice, c->st));
+    LAUNCH(c, launch_gather_scatter((const GatherJob*)d_job, 1, 1, nullptr, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+    if (applied_pixels) *applied_pixels = h_cnt;
+    return RBF_OK;
+}
+
+extern "C" int rbf_stream_download(rbf_stream* s, uint32_t frame, void* host_out) {
+    if (!s || !host_out || frame >= s->max_frames) return set_err(s ? s->c : nullptr, RBF_ERR_INVALID, "rbf_stream_download: bad argument");
+    rbf_ctx* c = s->c;
+    CK(c, cudaMemcpyAsync(host_out, s->d_frames + (size_t)frame * s->frame_stride, s->frame_bytes, cudaMemcpyDeviceToHost, c->st));
+    c->d2h += (int64_t)s->frame_bytes;
+    CK(c, cudaStreamSynchronize(c->st));
+    return RBF_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // NCCL (dlopen'ed so that single-GPU use needs no NCCL at all)
 // ------------------------------------------------------------------------------------------

@@ -1230,6 +1230,39 @@ __global__ void __launch_bounds__(1024) k_expand(const FrameJob* __restrict__ jo
 }
 
 // ------------------------------------------------------------------------------------------
+// N1 / N2: ordered gather of the changed pixels' values (ivc:810-842) and the scatter
+// that rebuilds the next frame (ivc:849-909).  One CTA per pair walks the mask words in order;
+// a block scan of the popcounts gives every set pixel its rank.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_gather_scatter(const GatherJob* __restrict__ jobs, int scatter,
+                                                          uint32_t* __restrict__ counts) {
+    const GatherJob J = jobs[blockIdx.x];
+    __shared__ uint32_t s_warp[33];
+    const uint32_t nwords = (J.npix + 31u) >> 5;
+    const uint32_t pb = J.pix_bytes;
+    uint32_t base = 0;
+    for (uint32_t w0 = 0; w0 < nwords; w0 += blockDim.x) {
+        const uint32_t w = w0 + threadIdx.x;
+        uint32_t m = (w < nwords) ? __ldg(J.mask + w) : 0u;
+        uint32_t tot;
+        uint32_t rank = base + block_excl_scan(__popc(m), s_warp, tot);
+        while (m) {
+            const uint32_t b = __ffs(m) - 1;
+            m &= m - 1u;
+            const size_t px = ((size_t)w << 5) + b;
+            if (scatter) {
+                for (uint32_t q = 0; q < pb; q++) J.out_frame[px * pb + q] = J.values[(size_t)rank * pb + q];
+            } else {
+                for (uint32_t q = 0; q < pb; q++) J.values[(size_t)rank * pb + q] = J.frame[px * pb + q];
+            }
+            rank++;
+        }
+        base += tot;
+    }
+    if (threadIdx.x == 0 && counts) counts[blockIdx.x] = base;
+}
+
+// ------------------------------------------------------------------------------------------
 // small utilities
 // ------------------------------------------------------------------------------------------
 __global__ void k_bitrev(uint32_t* __restrict__ w, size_t n) {
@@ -1491,6 +1524,11 @@ static inline unsigned grid_for(size_t n, unsigned block) {
     if (g > 148u * 16u) g = 148u * 16u;
     if (g < 1) g = 1;
     return (unsigned)g;
+}
+cudaError_t launch_gather_scatter(const GatherJob* d_jobs, int F, int scatter, uint32_t* d_counts, cudaStream_t st) {
+    if (F <= 0) return cudaSuccess;
+    k_gather_scatter<<<F, 1024, 0, st>>>(d_jobs, scatter, d_counts);
+    return cudaGetLastError();
 }
 cudaError_t launch_bitrev(uint32_t* d_words, size_t nwords, cudaStream_t st) {
     if (nwords == 0) return cudaSuccess;

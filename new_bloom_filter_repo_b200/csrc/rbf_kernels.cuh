@@ -36,6 +36,16 @@ struct PairJob {
     uint32_t* mask;       // n bits natural packing
 };
 
+struct GatherJob {
+    const uint32_t* mask;     // n bits, natural packing
+    const uint8_t* frame;     // gather: source (curr) frame; scatter: unused
+    uint8_t* values;          // gather: output; scatter: input (rank-ordered pixel values)
+    uint8_t* out_frame;       // scatter: destination frame (already holds the base frame)
+    uint32_t npix;
+    uint32_t pix_bytes;
+};
+
+
 // launchers (all asynchronous on `st`); return cudaError_t of the launch
 cudaError_t launch_threshold(const PairJob* d_pairs, int F, uint32_t npix, int channels, int sample_bytes,
                              int thr_int, int any_mode, uint32_t* d_ones, uint32_t* d_resid, int variant, int sm_count,
@@ -45,6 +55,7 @@ cudaError_t launch_query(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, 
                          uint32_t max_l_bits, int variant, int sm_count, int smem_bytes_cap, cudaStream_t st);
 cudaError_t launch_witness(const FrameJob* d_jobs, int F, uint32_t* d_wlen, cudaStream_t st);
 cudaError_t launch_expand(const FrameJob* d_jobs, int F, uint32_t* d_consumed, cudaStream_t st);
+cudaError_t launch_gather_scatter(const GatherJob* d_jobs, int F, int scatter, uint32_t* d_counts, cudaStream_t st);
 cudaError_t launch_bitrev(uint32_t* d_words, size_t nwords, cudaStream_t st);
 cudaError_t launch_unpack_bits(const uint32_t* d_words, uint8_t* d_out, size_t nbits, cudaStream_t st);
 cudaError_t launch_unpack_bits_msb(const uint32_t* d_words, uint8_t* d_out, size_t nbits, cudaStream_t st);

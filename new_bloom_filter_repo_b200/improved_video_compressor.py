@@ -199,37 +199,34 @@ class VideoFrameCompressor:
             _cabi.check(L.rbf_set_option(_cabi.ctx(), b"k1_only", 0), _cabi.ctx())
         _, _, flat = st.fetch(0)
         binary_diff = flat.reshape(pd.shape[0], pd.shape[1]).astype(np.uint8)
-        rows, cols = np.where(binary_diff == 1)
-        if is_color:
-            if self.use_direct_yuv and hasattr(curr_frame, "yuv_info"):
-                info = curr_frame.yuv_info                     # ivc:818-829 (uint8 truncation included)
-                changed = np.empty(len(rows) * cd.shape[2], dtype=np.uint8)
-                changed[0::3] = info["y_plane"][rows, cols]
-                changed[1::3] = info["u_plane"][rows, cols]
-                changed[2::3] = info["v_plane"][rows, cols]
-            else:
-                changed = cd[rows, cols, :].reshape(-1).astype(cd.dtype)   # ivc:832-839
+        vals = st.gather_changed(1)[0]                        # N1: ordered gather on the device (ivc:810-842)
+        if is_color and self.use_direct_yuv and hasattr(curr_frame, "yuv_info"):
+            changed = vals.astype(np.uint8)                   # ivc:825 allocates uint8: 16-bit samples are truncated there too
         else:
-            changed = cd[rows, cols].copy()                    # ivc:842
+            changed = vals.copy()                             # ivc:832-842 keep the frame dtype
         density = res.ones / binary_diff.size                  # ivc:845
         self._last_pair_result = res
         return binary_diff, changed, density
 
     def _apply_frame_diff(self, base_frame, diff_mask: np.ndarray, changed_values: np.ndarray):   # ivc:849-909
+        """N2: the scatter runs on the device (k_gather_scatter); the result is a copy of base_frame's type."""
         nxt = base_frame.copy()
-        rows, cols = np.where(diff_mask == 1)
         data = _frame_data(nxt)
-        if data.ndim == 3 and data.shape[2] > 1:
-            ch = data.shape[2]
-            if len(changed_values) == len(rows) * ch:          # ivc:882
-                pix = np.asarray(changed_values).reshape(-1, ch)
-                data[rows, cols] = pix
-                if self.use_direct_yuv and hasattr(nxt, "yuv_info"):
-                    nxt.yuv_info["y_plane"][rows, cols] = pix[:, 0]
-                    nxt.yuv_info["u_plane"][rows, cols] = pix[:, 1]
-                    nxt.yuv_info["v_plane"][rows, cols] = pix[:, 2]
-        elif len(rows) > 0:
-            data[rows, cols] = changed_values
+        vals = np.asarray(changed_values)
+        if data.dtype not in (np.uint8, np.uint16) or vals.dtype != data.dtype or not (data.ndim == 2 or data.shape[2] == 3):
+            rows, cols = np.where(diff_mask == 1)              # formats outside the device store: host indexing
+            ch = data.shape[2] if data.ndim == 3 else 1
+            if len(vals) == len(rows) * ch:
+                data[rows, cols] = vals.reshape(-1, ch) if ch > 1 else vals
+        else:
+            st = self._stream_for(data.shape, data.dtype)
+            st.upload(np.ascontiguousarray(data)[None], first=0)
+            st.apply_diff(0, 1, diff_mask, vals)               # value-count mismatch leaves the base unchanged (ivc:882)
+            data[...] = st.download(1)
+        if self.use_direct_yuv and hasattr(nxt, "yuv_info") and data.ndim == 3:
+            nxt.yuv_info["y_plane"] = data[:, :, 0].copy()
+            nxt.yuv_info["u_plane"] = data[:, :, 1].copy()
+            nxt.yuv_info["v_plane"] = data[:, :, 2].copy()
         return nxt
 
     def _compress_frame_differences(self, binary_diff: np.ndarray, changed_values: np.ndarray) -> Tuple[bytes, float]:
@@ -350,15 +347,14 @@ class ImprovedVideoCompressor:
                 st.upload(np.stack([datas[f] for f in need]))
                 thr = float(self.inter_frame_threshold)
                 res = st.encode([slot[i - 1] for i in idxs], [slot[i] for i in idxs], thr)
+                gathered = st.gather_changed(len(idxs))            # N1: changed values of every pair, one launch
                 for j, i in enumerate(idxs):
                     r = res[j]
                     if r.resid and self.inter_frame_mode != "lossless":
                         out[i] = None                              # not exactly representable: keyframe instead
                         continue
                     bm, wt, mask = st.fetch(j)
-                    cur = datas[i]
-                    sel = mask.reshape(shape[0], shape[1]).astype(bool)
-                    values = cur[sel].reshape(-1)                  # interleaved channel values of changed pixels
+                    values = gathered[j]                           # interleaved channel values of changed pixels
                     vz = zlib.compress(values.tobytes(), 9)
                     hdr = _INTER_TAG + struct.pack("<IIIBB", shape[0], shape[1], dtype.itemsize, ch, 1 if r.raw else 0)
                     body = struct.pack("<dIIQ", r.k, r.l, r.wlen, r.ones)
@@ -444,15 +440,20 @@ class ImprovedVideoCompressor:
             witness = np.unpackbits(wbytes)[:wlen]
             mask = BloomFilterCompressor().decompress(bitmap, witness, n, k)
         pdata = _frame_data(prev)
-        out = pdata.copy()
-        sel = mask.reshape(h, w).astype(bool)
-        if ch > 1:
-            out[sel] = values.reshape(-1, ch)
-        else:
-            out[sel] = values
-        if hasattr(prev, "yuv_info"):
-            return YUVFrame(out)
-        return out
+        st = getattr(self, "_dec_stream", None)
+        if st is None or (st.H, st.W, st.C, st.dtype) != (h, w, ch, np.dtype(dtype)):
+            st = FrameStream(h, w, ch, dtype, max_frames=2, max_pairs=1)
+            self._dec_stream, self._dec_slot, self._dec_src = st, 0, None
+        if self._dec_src is not prev:                             # previous frame is not the one resident on the device
+            st.upload(np.ascontiguousarray(pdata)[None], first=0)
+            self._dec_slot = 0
+        nxt_slot = 1 - self._dec_slot
+        st.apply_diff(self._dec_slot, nxt_slot, mask, values)     # N2: scatter on the device
+        out = st.download(nxt_slot)
+        self._dec_slot = nxt_slot
+        res = YUVFrame(out) if hasattr(prev, "yuv_info") else out
+        self._dec_src = res
+        return res
 
     def decompress_video(self, input_path: str = None, output_path: Optional[str] = None,
                          compressed_frames: List[bytes] = None, metadata: Dict = None) -> List[np.ndarray]:

@@ -106,6 +106,32 @@ class FrameStream:
         _cabi.check(_cabi.lib().rbf_stream_decode_verify(self._h, n, _cabi.ptr(out)), _cabi.ctx())
         return out
 
+    # ------------------------------------------------------------------ N1 / N2
+    def gather_changed(self, pairs: Optional[int] = None) -> List[np.ndarray]:
+        """Per encoded pair: interleaved channel values of the current frame at the mask's set positions (ivc:810-842)."""
+        n = self.pairs if pairs is None else int(pairs)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        _cabi.check(_cabi.lib().rbf_stream_gather_changed(self._h, n, None, 0, _cabi.ptr(offs)), _cabi.ctx())
+        buf = np.empty(int(offs[-1]), dtype=np.uint8)
+        if buf.size:
+            _cabi.check(_cabi.lib().rbf_stream_gather_changed(self._h, n, _cabi.ptr(buf), buf.size, _cabi.ptr(offs)), _cabi.ctx())
+        return [buf[int(offs[i]):int(offs[i + 1])].view(self.dtype) for i in range(n)]
+
+    def apply_diff(self, base_frame: int, out_frame: int, mask: np.ndarray, values: np.ndarray) -> int:
+        """store[out_frame] = store[base_frame] with masked pixels replaced by `values` (ivc:849-909); returns pixels applied."""
+        mk = np.packbits(np.ascontiguousarray(mask, dtype=np.uint8).reshape(-1), bitorder="little")
+        vals = np.ascontiguousarray(values).view(np.uint8).reshape(-1)
+        applied = C.c_uint64()
+        _cabi.check(_cabi.lib().rbf_stream_apply_diff(self._h, int(base_frame), int(out_frame), _cabi.ptr(mk),
+                                                      _cabi.ptr(vals) if vals.size else None, vals.size, C.byref(applied)), _cabi.ctx())
+        return int(applied.value)
+
+    def download(self, frame: int) -> np.ndarray:
+        shape = (self.H, self.W, self.C) if self.C > 1 else (self.H, self.W)
+        out = np.empty(shape, dtype=self.dtype)
+        _cabi.check(_cabi.lib().rbf_stream_download(self._h, int(frame), _cabi.ptr(out)), _cabi.ctx())
+        return out
+
     def stage_ms(self) -> dict:
         out = (C.c_double * 5)()
         _cabi.check(_cabi.lib().rbf_stream_stage_ms(self._h, out), _cabi.ctx())

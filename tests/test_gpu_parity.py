@@ -378,3 +378,41 @@ def test_nccl_allgather_single_rank(pkg):
     send.free(); recv.free()
     cabi.check(cabi.lib().rbf_nccl_destroy(cabi.ctx()), cabi.ctx())
     st.close()
+
+
+# ------------------------------------------------------------------ SURVEY 8(f) N1 / N2 on the device
+@pytest.mark.parametrize("shape,dtype", [((64, 64), np.uint8), ((37, 53), np.uint8), ((270, 480), np.uint16), ((1080, 1920), np.uint8)])
+def test_gather_changed_and_apply_diff_vs_oracle(pkg, shape, dtype):
+    from oracle import rbf_oracle as po
+    frames = synth_stream(shape[0], shape[1], 4, 77, [0.05, 0.3, 0.0], dtype)
+    st = pkg.FrameStream(shape[0], shape[1], 3, dtype, max_frames=6)
+    st.upload(frames)
+    res = st.encode_consecutive(4, 3.0)
+    gathered = st.gather_changed()
+    for t in range(3):
+        mask = po.frame_diff_mask(frames[t], frames[t + 1], 3.0)
+        rows, cols = np.where(mask == 1)
+        expect = frames[t + 1][rows, cols, :].reshape(-1)                 # ivc:810-842, native sample type
+        assert gathered[t].dtype == frames.dtype and np.array_equal(gathered[t], expect), t
+        assert res[t].ones == len(rows)
+        # N2: rebuild frame t+1 from frame t on the device (slot 4 <- slot t)
+        applied = st.apply_diff(t, 4, mask, gathered[t])
+        assert applied == len(rows)
+        want = po.apply_frame_diff(frames[t], mask, expect)
+        assert np.array_equal(st.download(4), want)
+        assert np.array_equal(want, frames[t + 1])                        # every channel moves together in this stream
+    # value-count mismatch leaves the base frame unchanged (ivc:882)
+    mask = po.frame_diff_mask(frames[0], frames[1], 3.0)
+    assert st.apply_diff(0, 5, mask, gathered[0][:-3]) == 0
+    assert np.array_equal(st.download(5), frames[0])
+    st.close()
+
+
+def test_vfc_apply_frame_diff_device_path(pkg):
+    vfc = pkg.VideoFrameCompressor(use_direct_yuv=True)
+    prev, curr = synth_pair(96, 128, 5, 0.1, np.uint8)
+    pf, cf = pkg.YUVFrame(prev), pkg.YUVFrame(curr)
+    mask, changed, _ = vfc._calculate_frame_diff(pf, cf, threshold=0.0)
+    rec = vfc._apply_frame_diff(pf, mask, changed)
+    assert np.array_equal(rec.data, curr) and np.array_equal(rec.yuv_info["u_plane"], curr[:, :, 1])
+    assert np.array_equal(pf.data, prev)                                  # the base is not modified
