@@ -24,6 +24,8 @@ static thread_local char g_err[512] = "";
 struct rbf_ctx {
     int device = -1;
     cudaStream_t st = nullptr;
+    cudaStream_t st_copy = nullptr;   // H2D of frame chunks in rbf_stream_encode_host
+    int host_chunk_frames = 32;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaDeviceProp prop;
     int sm_count = 0;
@@ -226,6 +228,7 @@ extern "C" void rbf_ctx_destroy(rbf_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->st) cudaStreamDestroy(c->st);
+    if (c->st_copy) cudaStreamDestroy(c->st_copy);
     delete c;
 }
 extern "C" const char* rbf_last_error(const rbf_ctx* c) { return c ? c->err : g_err; }
@@ -245,6 +248,7 @@ extern "C" int rbf_set_option(rbf_ctx* c, const char* key, int64_t v) {
     if (!strcmp(key, "k1_variant")) { c->k1_variant = (int)v; return RBF_OK; }
     if (!strcmp(key, "query_variant")) { c->query_variant = (int)(v < 0 ? 0 : (v > 3 ? 3 : v)); return RBF_OK; }
     if (!strcmp(key, "insert_variant")) { c->insert_variant = v ? 1 : 0; return RBF_OK; }
+    if (!strcmp(key, "host_chunk_frames")) { c->host_chunk_frames = (int)v; return RBF_OK; }
     if (!strcmp(key, "k1_only")) { c->k1_only = v ? 1 : 0; return RBF_OK; }
     if (!strcmp(key, "mask_mode")) { c->mask_mode = v ? 1 : 0; return RBF_OK; }
     if (!strcmp(key, "query_smem_bytes")) {
@@ -534,6 +538,7 @@ struct rbf_stream {
     uint32_t last_pairs = 0, last_max_l = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool staged = false;
+    std::vector<cudaEvent_t> ev_copy;
     std::vector<rbf_mask_info> last_infos;
 };
 
@@ -543,6 +548,7 @@ extern "C" void rbf_stream_destroy(rbf_stream* s) {
     cudaFree(s->d_frames); cudaFree(s->d_mask); cudaFree(s->d_bits); cudaFree(s->d_wit); cudaFree(s->d_pass); cudaFree(s->d_dec);
     cudaFree(s->d_jobs); cudaFree(s->d_pairs); cudaFree(s->d_prefix); cudaFree(s->d_ones); cudaFree(s->d_resid); cudaFree(s->d_wlen);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : s->ev_copy) if (e) cudaEventDestroy(e);
     cudaFreeHost(s->h_jobs); cudaFreeHost(s->h_pairs); cudaFreeHost(s->h_prefix); cudaFreeHost(s->h_ones); cudaFreeHost(s->h_resid); cudaFreeHost(s->h_wlen);
     delete s;
 }
@@ -570,13 +576,13 @@ extern "C" int rbf_stream_create(rbf_ctx* c, uint32_t H, uint32_t W, uint32_t C,
     dalloc((void**)&s->d_pass, s->pass_stride_w * 4 * max_pairs);
     dalloc((void**)&s->d_jobs, sizeof(FrameJob) * max_pairs);
     dalloc((void**)&s->d_pairs, sizeof(PairJob) * max_pairs);
-    dalloc((void**)&s->d_prefix, 4 * ((size_t)max_pairs + 1));
+    dalloc((void**)&s->d_prefix, 4 * (2 * (size_t)max_pairs + 4));
     dalloc((void**)&s->d_ones, 4 * (size_t)max_pairs);
     dalloc((void**)&s->d_resid, 4 * (size_t)max_pairs);
     dalloc((void**)&s->d_wlen, 4 * (size_t)max_pairs);
     halloc((void**)&s->h_jobs, sizeof(FrameJob) * max_pairs);
     halloc((void**)&s->h_pairs, sizeof(PairJob) * max_pairs);
-    halloc((void**)&s->h_prefix, 4 * ((size_t)max_pairs + 1));
+    halloc((void**)&s->h_prefix, 4 * (2 * (size_t)max_pairs + 4));
     halloc((void**)&s->h_ones, 4 * (size_t)max_pairs);
     halloc((void**)&s->h_resid, 4 * (size_t)max_pairs);
     halloc((void**)&s->h_wlen, 4 * (size_t)max_pairs);
@@ -621,53 +627,57 @@ static int threshold_to_int(double thr) {
     return (int)floor(thr);
 }
 
-static int stream_encode_async(rbf_stream* s, const uint32_t* prev_idx, const uint32_t* curr_idx, uint32_t pairs,
-                               double threshold, const rbf_seeds* sd, const double* kov, const uint64_t* lov) {
+// Encode pairs [first, first+count) (slots of all per-pair arrays); prev_idx/curr_idx are indexed from 0.
+// `pfx` is the slot of this range's century-prefix array (count+1 entries) inside h_prefix/d_prefix.
+static int stream_encode_range(rbf_stream* s, uint32_t first, uint32_t count, uint32_t pfx, const uint32_t* prev_idx,
+                               const uint32_t* curr_idx, double threshold, const rbf_seeds* sd, const double* kov,
+                               const uint64_t* lov, bool record_events) {
     rbf_ctx* c = s->c;
     const uint32_t n = (uint32_t)s->npix;
     int thr_int = threshold_to_int(threshold);
     if (s->S == 2 && threshold < -1.0) {               // int16 abs can be -32768 (ivc:801): keep exact floor
         thr_int = threshold < -40000.0 ? -40000 : (int)floor(threshold);
     }
-    for (uint32_t i = 0; i < pairs; i++) {
+    for (uint32_t i = 0; i < count; i++) {
         if (prev_idx[i] >= s->max_frames || curr_idx[i] >= s->max_frames)
-            return set_err(c, RBF_ERR_INVALID, "pair %u references a frame outside the store", i);
-        s->h_pairs[i].prev = s->d_frames + (size_t)prev_idx[i] * s->frame_stride;
-        s->h_pairs[i].curr = s->d_frames + (size_t)curr_idx[i] * s->frame_stride;
-        s->h_pairs[i].mask = s->d_mask + (size_t)i * s->mask_stride_w;
+            return set_err(c, RBF_ERR_INVALID, "pair %u references a frame outside the store", first + i);
+        PairJob& P = s->h_pairs[first + i];
+        P.prev = s->d_frames + (size_t)prev_idx[i] * s->frame_stride;
+        P.curr = s->d_frames + (size_t)curr_idx[i] * s->frame_stride;
+        P.mask = s->d_mask + (size_t)(first + i) * s->mask_stride_w;
     }
-    CK(c, cudaMemcpyAsync(s->d_pairs, s->h_pairs, sizeof(PairJob) * pairs, cudaMemcpyHostToDevice, c->st));
-    CK(c, cudaMemsetAsync(s->d_ones, 0, 4 * (size_t)pairs, c->st));
-    CK(c, cudaMemsetAsync(s->d_resid, 0, 4 * (size_t)pairs, c->st));
-    s->staged = false;
-    CK(c, cudaEventRecord(s->ev[0], c->st));
-    LAUNCH(c, launch_threshold(s->d_pairs, (int)pairs, n, (int)s->C, (int)s->S, thr_int, c->mask_mode, s->d_ones, s->d_resid, c->k1_variant,
-                               c->sm_count, c->st));
+    CK(c, cudaMemcpyAsync(s->d_pairs + first, s->h_pairs + first, sizeof(PairJob) * count, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemsetAsync(s->d_ones + first, 0, 4 * (size_t)count, c->st));
+    CK(c, cudaMemsetAsync(s->d_resid + first, 0, 4 * (size_t)count, c->st));
+    if (record_events) { s->staged = false; CK(c, cudaEventRecord(s->ev[0], c->st)); }
+    LAUNCH(c, launch_threshold(s->d_pairs + first, (int)count, n, (int)s->C, (int)s->S, thr_int, c->mask_mode, s->d_ones + first,
+                               s->d_resid + first, c->k1_variant, c->sm_count, c->st));
     if (c->k1_variant == 1) c->launches++;              // tail kernel
-    CK(c, cudaEventRecord(s->ev[1], c->st));
-    CK(c, cudaMemcpyAsync(s->h_ones, s->d_ones, 4 * (size_t)pairs, cudaMemcpyDeviceToHost, c->st));
-    CK(c, cudaMemcpyAsync(s->h_resid, s->d_resid, 4 * (size_t)pairs, cudaMemcpyDeviceToHost, c->st));
-    c->d2h += 8 * (int64_t)pairs;
+    if (record_events) CK(c, cudaEventRecord(s->ev[1], c->st));
+    CK(c, cudaMemcpyAsync(s->h_ones + first, s->d_ones + first, 4 * (size_t)count, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaMemcpyAsync(s->h_resid + first, s->d_resid + first, 4 * (size_t)count, cudaMemcpyDeviceToHost, c->st));
+    c->d2h += 8 * (int64_t)count;
     CK(c, cudaStreamSynchronize(c->st));               // the one host round trip: (p, k, l, T) need libm's log2
-    s->last_infos.assign(pairs, rbf_mask_info());
+    if (s->last_infos.size() < (size_t)first + count) s->last_infos.resize((size_t)first + count);
     const uint32_t ncent = (n + 99u) / 100u;
     uint32_t total_cent = 0, coded_pairs = 0, max_l = 0;
-    s->h_prefix[0] = 0;
-    for (uint32_t i = 0; i < pairs; i++) {
-        rbf_mask_info& in = s->last_infos[i];
+    uint32_t* hp = s->h_prefix + pfx;
+    hp[0] = 0;
+    for (uint32_t i = 0; i < count; i++) {
+        rbf_mask_info& in = s->last_infos[first + i];
         memset(&in, 0, sizeof in);
-        in.n = n; in.ones = s->h_ones[i]; in.resid = s->h_resid[i];
+        in.n = n; in.ones = s->h_ones[first + i]; in.resid = s->h_resid[first + i];
         double p, k; uint64_t l;
         int coded = rbf_optimal_params(n, in.ones, &p, &k, &l);
         in.p = p;
         if (kov && kov[i] > 0.0 && !(p >= kPStar)) { k = kov[i]; l = lov ? lov[i] : 0; coded = !(l == 0 || l >= n); }
-        FrameJob& J = s->h_jobs[i];
+        FrameJob& J = s->h_jobs[first + i];
         memset(&J, 0, sizeof J);
         J.n = n;
-        J.mask = s->d_mask + (size_t)i * s->mask_stride_w;
-        J.bits = s->d_bits + (size_t)i * s->mask_stride_w;
-        J.witness = s->d_wit + (size_t)i * s->mask_stride_w;
-        J.pass = s->d_pass + (size_t)i * s->pass_stride_w;
+        J.mask = s->d_mask + (size_t)(first + i) * s->mask_stride_w;
+        J.bits = s->d_bits + (size_t)(first + i) * s->mask_stride_w;
+        J.witness = s->d_wit + (size_t)(first + i) * s->mask_stride_w;
+        J.pass = s->d_pass + (size_t)(first + i) * s->pass_stride_w;
         if (coded) {
             job_set_filter(J, l, k, *sd);
             in.k = k; in.l = l; in.floor_k = J.floor_k; in.act_T = J.act_T;
@@ -676,26 +686,33 @@ static int stream_encode_async(rbf_stream* s, const uint32_t* prev_idx, const ui
         } else {
             in.raw = 1;
         }
-        s->h_prefix[i + 1] = total_cent;
+        hp[i + 1] = total_cent;
     }
-    s->last_pairs = pairs;
-    s->last_max_l = max_l;
+    if (first + count > s->last_pairs || first == 0) s->last_pairs = first + count;
+    if (max_l > s->last_max_l || first == 0) s->last_max_l = max_l;
     if (coded_pairs == 0 || c->k1_only) return RBF_OK;
-    CK(c, cudaMemcpyAsync(s->d_jobs, s->h_jobs, sizeof(FrameJob) * pairs, cudaMemcpyHostToDevice, c->st));
-    CK(c, cudaMemcpyAsync(s->d_prefix, s->h_prefix, 4 * ((size_t)pairs + 1), cudaMemcpyHostToDevice, c->st));
-    CK(c, cudaMemsetAsync(s->d_bits, 0, s->mask_stride_w * 4 * pairs, c->st));
-    CK(c, cudaMemsetAsync(s->d_wit, 0, s->mask_stride_w * 4 * pairs, c->st));
-    CK(c, cudaEventRecord(s->ev[2], c->st));
-    LAUNCH(c, launch_insert(s->d_jobs, (int)pairs, ncent, c->insert_variant, c->sm_count, c->st));
-    CK(c, cudaEventRecord(s->ev[3], c->st));
-    LAUNCH(c, launch_query(s->d_jobs, s->d_prefix, (int)pairs, total_cent, max_l, c->query_variant, c->sm_count, c->query_smem_cap, c->st));
-    CK(c, cudaEventRecord(s->ev[4], c->st));
-    LAUNCH(c, launch_witness(s->d_jobs, (int)pairs, s->d_wlen, c->st));
-    CK(c, cudaEventRecord(s->ev[5], c->st));
-    s->staged = true;
-    CK(c, cudaMemcpyAsync(s->h_wlen, s->d_wlen, 4 * (size_t)pairs, cudaMemcpyDeviceToHost, c->st));
-    c->d2h += 4 * (int64_t)pairs;
+    CK(c, cudaMemcpyAsync(s->d_jobs + first, s->h_jobs + first, sizeof(FrameJob) * count, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemcpyAsync(s->d_prefix + pfx, hp, 4 * ((size_t)count + 1), cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemsetAsync(s->d_bits + (size_t)first * s->mask_stride_w, 0, s->mask_stride_w * 4 * count, c->st));
+    CK(c, cudaMemsetAsync(s->d_wit + (size_t)first * s->mask_stride_w, 0, s->mask_stride_w * 4 * count, c->st));
+    if (record_events) CK(c, cudaEventRecord(s->ev[2], c->st));
+    LAUNCH(c, launch_insert(s->d_jobs + first, (int)count, ncent, c->insert_variant, c->sm_count, c->st));
+    if (record_events) CK(c, cudaEventRecord(s->ev[3], c->st));
+    LAUNCH(c, launch_query(s->d_jobs + first, s->d_prefix + pfx, (int)count, total_cent, max_l, c->query_variant, c->sm_count,
+                           c->query_smem_cap, c->st));
+    if (record_events) CK(c, cudaEventRecord(s->ev[4], c->st));
+    LAUNCH(c, launch_witness(s->d_jobs + first, (int)count, s->d_wlen + first, c->st));
+    if (record_events) { CK(c, cudaEventRecord(s->ev[5], c->st)); s->staged = true; }
+    CK(c, cudaMemcpyAsync(s->h_wlen + first, s->d_wlen + first, 4 * (size_t)count, cudaMemcpyDeviceToHost, c->st));
+    c->d2h += 4 * (int64_t)count;
     return RBF_OK;
+}
+
+static int stream_encode_async(rbf_stream* s, const uint32_t* prev_idx, const uint32_t* curr_idx, uint32_t pairs,
+                               double threshold, const rbf_seeds* sd, const double* kov, const uint64_t* lov) {
+    s->last_infos.clear();
+    s->last_pairs = 0; s->last_max_l = 0;
+    return stream_encode_range(s, 0, pairs, 0, prev_idx, curr_idx, threshold, sd, kov, lov, true);
 }
 
 extern "C" int rbf_stream_encode(rbf_stream* s, const uint32_t* prev_idx, const uint32_t* curr_idx, uint32_t pairs,
@@ -744,25 +761,57 @@ extern "C" int rbf_stream_encode_host(rbf_stream* s, const void* host_frames, ui
     const uint32_t pairs = nframes - 1;
     if (nframes > s->max_frames || pairs > s->max_pairs) return set_err(c, RBF_ERR_INVALID, "stream too small for %u frames", nframes);
     CK(c, cudaSetDevice(c->device));
-    CK(c, cudaMemcpy2DAsync(s->d_frames, s->frame_stride, host_frames, s->frame_bytes, s->frame_bytes, nframes,
-                            cudaMemcpyHostToDevice, c->st));
-    c->h2d += (int64_t)s->frame_bytes * nframes;
-    std::vector<uint32_t> pi(pairs), ci(pairs);
-    for (uint32_t i = 0; i < pairs; i++) { pi[i] = i; ci[i] = i + 1; }
-    int rc = stream_encode_async(s, pi.data(), ci.data(), pairs, threshold, sd, nullptr, nullptr);
-    if (rc) return rc;
-    const size_t stride = s->mask_stride_w * 4;
-    if (bitmaps && bitmap_slot) {
-        const size_t w = bitmap_slot < stride ? bitmap_slot : stride;
-        CK(c, cudaMemcpy2DAsync(bitmaps, bitmap_slot, s->d_bits, stride, w, pairs, cudaMemcpyDeviceToHost, c->st));
-        c->d2h += (int64_t)w * pairs;
+    if (!c->st_copy) CK(c, cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+    // chunks of frames: all H2D copies are queued on the copy stream up front (pinned source), the compute stream
+    // encodes a chunk's pairs as soon as its frames have landed, so PCIe transfer and kernels overlap
+    const uint32_t CH = c->host_chunk_frames > 1 ? (uint32_t)c->host_chunk_frames : 32u;
+    const uint32_t nchunks = (nframes + CH - 1) / CH;
+    while (s->ev_copy.size() < nchunks) { cudaEvent_t e; CK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); s->ev_copy.push_back(e); }
+    const uint8_t* src = (const uint8_t*)host_frames;
+    for (uint32_t k = 0; k < nchunks; k++) {
+        const uint32_t f0 = k * CH, f1 = (f0 + CH < nframes) ? f0 + CH : nframes;
+        CK(c, cudaMemcpy2DAsync(s->d_frames + (size_t)f0 * s->frame_stride, s->frame_stride, src + (size_t)f0 * s->frame_bytes,
+                                s->frame_bytes, s->frame_bytes, f1 - f0, cudaMemcpyHostToDevice, c->st_copy));
+        CK(c, cudaEventRecord(s->ev_copy[k], c->st_copy));
     }
-    if (witness && witness_slot) {
-        const size_t w = witness_slot < stride ? witness_slot : stride;
-        CK(c, cudaMemcpy2DAsync(witness, witness_slot, s->d_wit, stride, w, pairs, cudaMemcpyDeviceToHost, c->st));
-        c->d2h += (int64_t)w * pairs;
+    c->h2d += (int64_t)s->frame_bytes * nframes;
+    s->last_infos.clear();
+    s->last_pairs = 0; s->last_max_l = 0;
+    const size_t stride = s->mask_stride_w * 4;
+    std::vector<uint32_t> pi, ci;
+    for (uint32_t k = 0; k < nchunks; k++) {
+        const uint32_t f0 = k * CH, f1 = (f0 + CH < nframes) ? f0 + CH : nframes;
+        const uint32_t p0 = f0 == 0 ? 0 : f0 - 1, p1 = f1 - 1;      // pairs (i, i+1) whose current frame is in this chunk
+        if (p1 <= p0) continue;
+        const uint32_t cnt = p1 - p0;
+        pi.resize(cnt); ci.resize(cnt);
+        for (uint32_t i = 0; i < cnt; i++) { pi[i] = p0 + i; ci[i] = p0 + i + 1; }
+        CK(c, cudaStreamWaitEvent(c->st, s->ev_copy[k], 0));
+        int rc = stream_encode_range(s, p0, cnt, p0 + k, pi.data(), ci.data(), threshold, sd, nullptr, nullptr, false);
+        if (rc) return rc;
+        if (bitmaps && bitmap_slot) {
+            const size_t w = bitmap_slot < stride ? bitmap_slot : stride;
+            CK(c, cudaMemcpy2DAsync(bitmaps + (size_t)p0 * bitmap_slot, bitmap_slot, (const uint8_t*)s->d_bits + (size_t)p0 * stride, stride,
+                                    w, cnt, cudaMemcpyDeviceToHost, c->st));
+            c->d2h += (int64_t)w * cnt;
+        }
+        if (witness && witness_slot) {
+            const size_t w = witness_slot < stride ? witness_slot : stride;
+            CK(c, cudaMemcpy2DAsync(witness + (size_t)p0 * witness_slot, witness_slot, (const uint8_t*)s->d_wit + (size_t)p0 * stride, stride,
+                                    w, cnt, cudaMemcpyDeviceToHost, c->st));
+            c->d2h += (int64_t)w * cnt;
+        }
     }
     CK(c, cudaStreamSynchronize(c->st));
+    // one contiguous prefix array for later decode_verify over all pairs
+    {
+        const uint32_t ncent = (uint32_t)((s->npix + 99) / 100);
+        uint32_t tot = 0;
+        s->h_prefix[0] = 0;
+        for (uint32_t i = 0; i < pairs; i++) { if (!s->last_infos[i].raw) tot += ncent; s->h_prefix[i + 1] = tot; }
+        CK(c, cudaMemcpyAsync(s->d_prefix, s->h_prefix, 4 * ((size_t)pairs + 1), cudaMemcpyHostToDevice, c->st));
+        CK(c, cudaStreamSynchronize(c->st));
+    }
     for (uint32_t i = 0; i < pairs; i++) {
         if (!s->last_infos[i].raw) s->last_infos[i].wlen = s->h_wlen[i];
         if (infos) infos[i] = s->last_infos[i];

@@ -416,3 +416,27 @@ def test_vfc_apply_frame_diff_device_path(pkg):
     rec = vfc._apply_frame_diff(pf, mask, changed)
     assert np.array_equal(rec.data, curr) and np.array_equal(rec.yuv_info["u_plane"], curr[:, :, 1])
     assert np.array_equal(pf.data, prev)                                  # the base is not modified
+
+
+def test_encode_host_chunked_matches_resident(pkg, co):
+    """The end-to-end call (host frames in, packed outputs out, chunked H2D overlapped with the kernels) gives the same
+    bytes as the device-resident encode, across chunk boundaries."""
+    L, ctx = pkg._cabi.lib(), pkg._cabi.ctx()
+    frames = synth_stream(120, 160, 11, 91, [0.05, 0.2, 0.0, 0.4, 0.01])
+    st = pkg.FrameStream(120, 160, 3, np.uint8, max_frames=11)
+    st.upload(frames)
+    ref = st.encode_consecutive(11, 3.0)
+    want = [st.fetch(t, want_mask=False)[:2] for t in range(10)]
+    slot_b = (max(r.l for r in ref) + 7) // 8 + 16
+    slot_w = (max(r.wlen for r in ref) + 7) // 8 + 16
+    for chunk in (2, 3, 32):
+        pkg._cabi.check(L.rbf_set_option(ctx, b"host_chunk_frames", chunk), ctx)
+        ob = np.zeros((10, slot_b), np.uint8); ow = np.zeros((10, slot_w), np.uint8)
+        res = st.encode_host(frames, 3.0, bitmap_slot=slot_b, witness_slot=slot_w, out_bitmaps=ob, out_witness=ow)
+        for t in range(10):
+            assert (res[t].raw, res[t].l, res[t].wlen, res[t].ones, res[t].k) == (ref[t].raw, ref[t].l, ref[t].wlen, ref[t].ones, ref[t].k)
+            if not res[t].raw:
+                assert np.array_equal(ob[t, : len(want[t][0])], want[t][0]) and np.array_equal(ow[t, : len(want[t][1])], want[t][1])
+        assert not st.decode_verify().any()
+    L.rbf_set_option(ctx, b"host_chunk_frames", 32)
+    st.close()
