@@ -286,6 +286,12 @@ def run_ours(args):
         peak, peak_src = measured_peaks()
         q_ms = stage["k3_query"]
         coded_px = sum(r.n for r in res if not r.raw)
+        traffic = None
+        try:                                     # dram bytes per launch of k_query2 from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r01_k_query2_traffic.json")) as f:
+                traffic = json.load(f)["dram_bytes_per_pair"] * sum(1 for r in res if not r.raw)
+        except Exception:
+            pass
         achieved = coded_px * BYTES_PER_PIXEL / (q_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -297,10 +303,10 @@ def run_ours(args):
                        "height": H, "width": W, "frames": F, "pairs_per_gpu": pairs, "parallelism": "frame-sharded x%d" % world,
                        "l2_policy": "inputs larger than L2: %.2f GB of frames per step, no flush needed" % (F * n * 3 / 1e9),
                        "k1_variant": "tma-bulk-ring" if args.k1_variant == 1 else "ldg256",
-                       "query_variant": "staged-queues" if args.query_variant == 1 else "per-lane",
+                       "query_variant": {0: "per-lane", 1: "staged-rings", 2: "staged-rings+dsmem-cluster", 3: "dense-A+B"}.get(args.query_variant),
                        "mean_l_bits": float(np.mean([r.l for r in res])), "mean_witness_bits": float(np.mean([r.wlen for r in res]))},
-            "roofline": {"bound": "hbm", "kernel": "k_query", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "k_query2", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": coded_px * BYTES_PER_PIXEL, "launch_ms": q_ms,
                          "pipeline_frac": value * 1e6 * BYTES_PER_PIXEL / 1e9 / world / peak,
                          "stage_ms": stage},
