@@ -193,6 +193,23 @@ RBF_HD uint64_t finish_t(uint64_t D, uint64_t seed, uint32_t y) {
     return avalanche(byte_step(D, 48u + y));
 }
 
+
+// rotl(x ^ b, 11) == rotl(x, 11) ^ rotl(b, 11): for the kinds whose last character is a single-byte step the
+// rotation of the decade state is hoisted out of the per-position work and the ten per-digit constants
+// rotl((48 + y) * P5, 11) come from a table.
+RBF_HD constexpr uint64_t rot_digit_const(uint32_t y) {
+    return (((uint64_t)(48u + y) * XP5) << 11) | (((uint64_t)(48u + y) * XP5) >> 53);
+}
+template <int KIND> RBF_HD constexpr bool kind_ends_in_byte() { return KIND == K_BB || KIND == K_4B || KIND == K_8B; }
+// Dx = rotl(decade_state, 11) for byte kinds, the plain decade state otherwise
+template <int KIND>
+RBF_HD uint64_t decade_prep(uint64_t D) { return kind_ends_in_byte<KIND>() ? rotl64(D, 11) : D; }
+template <int KIND>
+RBF_HD uint64_t finish_prep(uint64_t Dx, uint64_t seed, uint32_t y, uint64_t rot_const) {
+    if (kind_ends_in_byte<KIND>()) return avalanche((Dx ^ rot_const) * XP1);
+    return finish_t<KIND>(Dx, seed, y);
+}
+
 // ---------------------------------------------------------------------------------
 // h mod m for a per-frame constant m (the Bloom size l).  Barrett with M = floor(2^64/m),
 // truncated partial products: q_est in [Q-3, Q], so r_est = h - q_est*m < 4m fits 32 bits

@@ -653,9 +653,12 @@ __global__ void __launch_bounds__(QT) k_query(const FrameJob* __restrict__ jobs,
 // false negatives) and skip the hashing.  Results are identical to the per-lane form above.
 // ------------------------------------------------------------------------------------------
 constexpr int Q2_WARPS = 24;
+__constant__ uint64_t c_rot_digit[16] = {rot_digit_const(0), rot_digit_const(1), rot_digit_const(2), rot_digit_const(3),
+                                         rot_digit_const(4), rot_digit_const(5), rot_digit_const(6), rot_digit_const(7),
+                                         rot_digit_const(8), rot_digit_const(9), 0, 0, 0, 0, 0, 0};
 constexpr int Q2_THREADS = Q2_WARPS * 32;
 constexpr int Q2_RING = 64;                               // entries per ring (two drains' worth)
-constexpr int Q2_WARP_WORDS = (Q2_RING * 16 + Q2_RING * 8 + 32 * 16) / 4;   // B ring, C ring, pass accumulators
+constexpr int Q2_WARP_WORDS = (Q2_RING * 16 + Q2_RING * 8 + 32 * 16 + 128) / 4;   // B ring, C ring, pass accumulators, digit table
 
 // explicit shared-space accesses (32-bit shared addresses): no generic-pointer resolution in the hot loops
 __device__ __forceinline__ void sts128_if(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, bool p) {
@@ -742,7 +745,8 @@ __device__ __forceinline__ void drain_stages(const FilterK& K, uint32_t sm_addr,
         const uint4 r = lds128(qb_addr + 16u * ((R.qb_head + lane) & (Q2_RING - 1)));
         R.qb_head = (R.qb_head + nb) & (Q2_RING - 1);
         R.qb_cnt -= nb;
-        const uint32_t stepm = have ? mod_fast(finish_t<KIND>((uint64_t)r.z | ((uint64_t)r.w << 32), K.s2, r.y & 15u), K.fm) : 0u;
+        const uint64_t rbB = kind_ends_in_byte<KIND>() ? ({ const uint2 t = lds64(pacc_addr + 512u + 8u * (r.y & 15u)); (uint64_t)t.x | ((uint64_t)t.y << 32); }) : 0ull;
+        const uint32_t stepm = have ? mod_fast(finish_prep<KIND>((uint64_t)r.z | ((uint64_t)r.w << 32), K.s2, r.y & 15u, rbB), K.fm) : 0u;
         uint32_t idx = have ? r.x : 0u;
         uint32_t ok = have ? 1u : 0u;
         if (FKT > 0) {                                               // floor_k known at compile time: straight-line probes
@@ -795,26 +799,26 @@ __device__ __noinline__ void query_slab_staged(const FilterK K, uint32_t sm_addr
     const Century cen = make_century(active ? c : slab_c0);
     const uint64_t C1 = century_state(cen, K.s1), C2 = century_state(cen, K.s2), CA = century_state(cen, K.sA);
     const uint32_t nvalid = active ? min(100u, n - 100u * c) : 0u;
-    Bits128 mb; mb.lo = 0; mb.hi = 0;
-    if (active && mask != nullptr) mb = load_bits100(mask, c, nvalid);
     // positions that need no hashing: known members (mask bit set) and positions beyond n
-    uint64_t skip_lo = mb.lo, skip_hi = mb.hi;
+    uint64_t skip_lo = 0, skip_hi = 0;
+    if (active && mask != nullptr) { const Bits128 mb = load_bits100(mask, c, nvalid); skip_lo = mb.lo; skip_hi = mb.hi; }
+    if (lane < 10u) sts64_if(pacc_addr + 512u + 8u * lane, (uint32_t)c_rot_digit[lane], (uint32_t)(c_rot_digit[lane] >> 32), true);
     if (nvalid < 64u) { skip_hi = ~0ull; skip_lo |= ~((1ull << nvalid) - 1ull); }
     else skip_hi |= ~((1ull << (nvalid - 64u)) - 1ull);
     const uint32_t lt = (1u << lane) - 1u;
     RingState R; R.qb_head = 0; R.qb_cnt = 0; R.qc_head = 0; R.qc_cnt = 0;
 #pragma unroll 1
     for (uint32_t x = 0; x < 10u; x++) {
-        const uint64_t D1 = decade_state_t<KIND>(C1, K.s1, x);
-        const uint64_t D2 = decade_state_t<KIND>(C2, K.s2, x);
+        const uint64_t D1 = decade_prep<KIND>(decade_state_t<KIND>(C1, K.s1, x));   // rotation hoisted for byte kinds
+        const uint64_t D2 = decade_prep<KIND>(decade_state_t<KIND>(C2, K.s2, x));
         const uint32_t p0 = 10u * x;                                 // bits [p0, p0+10) of the 128-bit skip set
         const uint64_t sh = (p0 < 64u) ? ((skip_lo >> p0) | (p0 ? (skip_hi << (64u - p0)) : 0ull)) : (skip_hi >> (p0 - 64u));
         const uint32_t skip10 = (uint32_t)sh & 0x3ffu;
         const uint32_t tagx = (lane << 8) | (x << 4);
 #pragma unroll 1
         for (uint32_t y = 0; y < 10u; y += 2u) {                     // ---- stage A: two positions per lane (ILP)
-            const uint32_t idxA = mod_fast(finish_t<KIND>(D1, K.s1, y), K.fm);
-            const uint32_t idxB = mod_fast(finish_t<KIND>(D1, K.s1, y + 1u), K.fm);
+            const uint32_t idxA = mod_fast(finish_prep<KIND>(D1, K.s1, y, c_rot_digit[y]), K.fm);
+            const uint32_t idxB = mod_fast(finish_prep<KIND>(D1, K.s1, y + 1u, c_rot_digit[y + 1u]), K.fm);
             const uint32_t bA = probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idxA);
             const uint32_t bB = probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idxB);
             const bool svA = (bA & ~(skip10 >> y) & 1u) != 0u;
@@ -837,7 +841,10 @@ __device__ __noinline__ void query_slab_staged(const FilterK K, uint32_t sm_addr
     uint4 acc = lds128(pacc_addr + 16u * lane);
     sts128_if(pacc_addr + 16u * lane, 0u, 0u, 0u, 0u, true);
     if (active) {
-        acc.x |= (uint32_t)mb.lo; acc.y |= (uint32_t)(mb.lo >> 32); acc.z |= (uint32_t)mb.hi; acc.w |= (uint32_t)(mb.hi >> 32);
+        if (mask != nullptr) {                                       // known members pass (no false negatives); reloaded to save registers
+            const Bits128 mb = load_bits100(mask, c, nvalid);
+            acc.x |= (uint32_t)mb.lo; acc.y |= (uint32_t)(mb.lo >> 32); acc.z |= (uint32_t)mb.hi; acc.w |= (uint32_t)(mb.hi >> 32);
+        }
         pass4[c] = acc;
     }
     __syncwarp();
