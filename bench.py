@@ -55,10 +55,18 @@ def fill_stream(frames: np.ndarray, seed: int, one_in: int = 20) -> None:
     frames[0, :, :, 1] = base // 2 + 7
     frames[0, :, :, 2] = base // 3 + 90
     frames[0] += rng.integers(0, 8, (h, w, 3), dtype=np.uint8)
-    for t in range(1, nfr):
+    from concurrent.futures import ThreadPoolExecutor
+
+    def delta(t):                                    # independent of the other frames: generated in parallel
         r = np.random.default_rng(seed + t)
-        d = (r.integers(0, one_in, (h, w), dtype=np.uint8) == 0).view(np.uint8) * np.uint8(64)
-        np.add(frames[t - 1], d[:, :, None], out=frames[t])      # uint8 arithmetic wraps
+        return (r.integers(0, one_in, (h, w), dtype=np.uint8) == 0).view(np.uint8) * np.uint8(64)
+
+    workers = max(1, min(16, (os.cpu_count() or 2) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
+    with ThreadPoolExecutor(workers) as ex:
+        for t0 in range(1, nfr, 32):
+            ts = list(range(t0, min(nfr, t0 + 32)))
+            for t, d in zip(ts, ex.map(delta, ts)):
+                np.add(frames[t - 1], d[:, :, None], out=frames[t])      # uint8 arithmetic wraps
 
 
 class ClockSampler:

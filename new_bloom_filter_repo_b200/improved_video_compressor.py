@@ -104,8 +104,10 @@ class BloomFilterCompressor:
         """-> (bloom_filter_bitmap, witness, density, input_length, compression_ratio)"""
         arr = np.asarray(binary_input)
         n = len(arr)
-        if n == 0:
-            raise ValueError("empty input")
+        if n == 0:                                            # the reference divides 0/0 -> nan and falls through to the
+            with np.errstate(invalid="ignore", divide="ignore"):   # raw-passthrough branch (ivc:212, ivc:188-189, ivc:223-225)
+                p = np.float64(0.0) / np.float64(0.0)
+            return binary_input, [], p, 0, 1.0
         m8 = np.ascontiguousarray(arr, dtype=np.uint8)
         if m8.size and m8.max() > 1:
             raise ValueError("binary_input must hold 0/1 values")

@@ -440,3 +440,15 @@ def test_encode_host_chunked_matches_resident(pkg, co):
         assert not st.decode_verify().any()
     L.rbf_set_option(ctx, b"host_chunk_frames", 32)
     st.close()
+
+
+def test_compress_empty_and_constant_inputs(pkg):
+    comp = pkg.BloomFilterCompressor()
+    empty = np.zeros(0, dtype=np.uint8)
+    bitmap, witness, p, n, ratio = comp.compress(empty)          # reference: 0/0 -> nan -> raw passthrough
+    assert bitmap is empty and witness == [] and np.isnan(p) and n == 0 and ratio == 1.0
+    ones = np.ones(777, dtype=np.uint8)
+    bitmap, witness, p, n, ratio = comp.compress(ones)           # p = 1 >= P*  (ivc:215-218)
+    assert bitmap is ones and witness == [] and p == 1.0 and ratio == 1.0
+    with pytest.raises(ValueError):
+        comp.compress(np.full(10, 2, dtype=np.uint8))            # not a 0/1 vector
