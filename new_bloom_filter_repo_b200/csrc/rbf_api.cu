@@ -452,7 +452,7 @@ extern "C" int rbf_compress_mask(rbf_ctx* c, const uint8_t* mask, uint64_t n, co
     CK(c, cudaMemsetAsync(d_wit, 0, mw * 4, c->st));
     LAUNCH(c, launch_insert(d_job, 1, ncent, c->insert_variant, c->sm_count, c->st));
     LAUNCH(c, launch_query(d_job, d_prefix, 1, ncent, (uint32_t)l, c->query_variant, c->sm_count, c->query_smem_cap, c->st));
-    LAUNCH(c, launch_witness(d_job, 1, d_cnt + 1, c->st));
+    LAUNCH(c, launch_witness(d_job, 1, ncent, c->sm_count, (uint32_t*)((uint8_t*)d_small + 1024), d_cnt + 1, c->st)); c->launches += 2;
     CK(c, cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, c->st)); c->d2h += 16;
     CK(c, cudaStreamSynchronize(c->st));
     info->wlen = h_cnt[1];
@@ -508,7 +508,7 @@ extern "C" int rbf_decompress_mask(rbf_ctx* c, const uint8_t* bitmap, uint64_t l
     CK(c, cudaMemcpyAsync(d_job, &J, sizeof J, cudaMemcpyHostToDevice, c->st));
     CK(c, cudaMemcpyAsync(d_prefix, h_prefix, 8, cudaMemcpyHostToDevice, c->st));
     LAUNCH(c, launch_query(d_job, d_prefix, 1, ncent, (uint32_t)l, c->query_variant, c->sm_count, c->query_smem_cap, c->st));
-    LAUNCH(c, launch_expand(d_job, 1, d_cnt, c->st));
+    LAUNCH(c, launch_expand(d_job, 1, ncent, c->sm_count, (uint32_t*)((uint8_t*)d_small + 1024), d_cnt, c->st)); c->launches += 1;
     LAUNCH(c, launch_unpack_bits((const uint32_t*)d_out, (uint8_t*)d_bytes, n, c->st));
     uint32_t h_cnt = 0;
     CK(c, cudaMemcpyAsync(out, d_bytes, n, cudaMemcpyDeviceToHost, c->st)); c->d2h += n;
@@ -530,7 +530,7 @@ struct rbf_stream {
     uint32_t *d_mask = nullptr, *d_bits = nullptr, *d_wit = nullptr, *d_pass = nullptr, *d_dec = nullptr;
     FrameJob* d_jobs = nullptr;
     PairJob* d_pairs = nullptr;
-    uint32_t *d_prefix = nullptr, *d_ones = nullptr, *d_resid = nullptr, *d_wlen = nullptr;
+    uint32_t *d_prefix = nullptr, *d_ones = nullptr, *d_resid = nullptr, *d_wlen = nullptr, *d_chunkcnt = nullptr;
     // pinned host mirrors
     FrameJob* h_jobs = nullptr;
     PairJob* h_pairs = nullptr;
@@ -546,7 +546,7 @@ extern "C" void rbf_stream_destroy(rbf_stream* s) {
     if (!s) return;
     cudaSetDevice(s->c->device);
     cudaFree(s->d_frames); cudaFree(s->d_mask); cudaFree(s->d_bits); cudaFree(s->d_wit); cudaFree(s->d_pass); cudaFree(s->d_dec);
-    cudaFree(s->d_jobs); cudaFree(s->d_pairs); cudaFree(s->d_prefix); cudaFree(s->d_ones); cudaFree(s->d_resid); cudaFree(s->d_wlen);
+    cudaFree(s->d_jobs); cudaFree(s->d_pairs); cudaFree(s->d_prefix); cudaFree(s->d_ones); cudaFree(s->d_resid); cudaFree(s->d_wlen); cudaFree(s->d_chunkcnt);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     for (auto& e : s->ev_copy) if (e) cudaEventDestroy(e);
     cudaFreeHost(s->h_jobs); cudaFreeHost(s->h_pairs); cudaFreeHost(s->h_prefix); cudaFreeHost(s->h_ones); cudaFreeHost(s->h_resid); cudaFreeHost(s->h_wlen);
@@ -580,6 +580,7 @@ extern "C" int rbf_stream_create(rbf_ctx* c, uint32_t H, uint32_t W, uint32_t C,
     dalloc((void**)&s->d_ones, 4 * (size_t)max_pairs);
     dalloc((void**)&s->d_resid, 4 * (size_t)max_pairs);
     dalloc((void**)&s->d_wlen, 4 * (size_t)max_pairs);
+    dalloc((void**)&s->d_chunkcnt, 4 * 32 * (size_t)max_pairs);
     halloc((void**)&s->h_jobs, sizeof(FrameJob) * max_pairs);
     halloc((void**)&s->h_pairs, sizeof(PairJob) * max_pairs);
     halloc((void**)&s->h_prefix, 4 * (2 * (size_t)max_pairs + 4));
@@ -701,7 +702,8 @@ static int stream_encode_range(rbf_stream* s, uint32_t first, uint32_t count, ui
     LAUNCH(c, launch_query(s->d_jobs + first, s->d_prefix + pfx, (int)count, total_cent, max_l, c->query_variant, c->sm_count,
                            c->query_smem_cap, c->st));
     if (record_events) CK(c, cudaEventRecord(s->ev[4], c->st));
-    LAUNCH(c, launch_witness(s->d_jobs + first, (int)count, s->d_wlen + first, c->st));
+    LAUNCH(c, launch_witness(s->d_jobs + first, (int)count, ncent, c->sm_count, s->d_chunkcnt + 32 * (size_t)first, s->d_wlen + first, c->st));
+    c->launches += 2;                                   // pass-count + finalize kernels
     if (record_events) { CK(c, cudaEventRecord(s->ev[5], c->st)); s->staged = true; }
     CK(c, cudaMemcpyAsync(s->h_wlen + first, s->d_wlen + first, 4 * (size_t)count, cudaMemcpyDeviceToHost, c->st));
     c->d2h += 4 * (int64_t)count;
@@ -839,7 +841,8 @@ extern "C" int rbf_stream_decode_verify(rbf_stream* s, uint32_t pairs, uint64_t*
     CK(c, cudaMemcpyAsync(s->d_jobs, s->h_jobs, sizeof(FrameJob) * pairs, cudaMemcpyHostToDevice, c->st));
     const uint32_t total_cent = s->h_prefix[pairs];
     LAUNCH(c, launch_query(s->d_jobs, s->d_prefix, (int)pairs, total_cent, s->last_max_l, c->query_variant, c->sm_count, c->query_smem_cap, c->st));
-    LAUNCH(c, launch_expand(s->d_jobs, (int)pairs, s->d_wlen, c->st));
+    LAUNCH(c, launch_expand(s->d_jobs, (int)pairs, (uint32_t)((s->npix + 99) / 100), c->sm_count, s->d_chunkcnt, s->d_wlen, c->st));
+    c->launches += 1;
     void* d_cnt; int rc;
     if ((rc = scratch_get(c, 7, 4 * (size_t)pairs + 4096, &d_cnt))) return rc;
     CK(c, cudaMemsetAsync(d_cnt, 0, 4 * (size_t)pairs, c->st));

@@ -1142,18 +1142,47 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
 // passing positions (ivc:253), concatenated.  Finishes by converting witness and bit array
 // to np.packbits order in place (ivc:945, ivc:951).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_witness(const FrameJob* __restrict__ jobs, uint32_t* __restrict__ wlen_out) {
-    const FrameJob& J = jobs[blockIdx.x];
+// pass counts per (frame, chunk of centuries): lets several CTAs work on one frame, each knowing how many passing
+// positions precede its chunk
+__global__ void __launch_bounds__(256) k_pass_count(const FrameJob* __restrict__ jobs, uint32_t chunks, uint32_t* __restrict__ counts) {
+    const FrameJob& J = jobs[blockIdx.y];
+    __shared__ uint32_t s_c[8];
+    uint32_t c = 0;
+    if (J.l != 0) {
+        const uint32_t ncent = (J.n + 99u) / 100u;
+        const uint32_t c0 = (uint32_t)(((uint64_t)ncent * blockIdx.x) / chunks), c1 = (uint32_t)(((uint64_t)ncent * (blockIdx.x + 1)) / chunks);
+        const uint4* pass4 = reinterpret_cast<const uint4*>(J.pass);
+        for (uint32_t i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+            const uint4 p = pass4[i];
+            c += __popc(p.x) + __popc(p.y) + __popc(p.z) + __popc(p.w);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 8; i++) t += s_c[i];
+        counts[blockIdx.y * chunks + blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_witness(const FrameJob* __restrict__ jobs, uint32_t chunks,
+                                                  const uint32_t* __restrict__ counts, uint32_t* __restrict__ wlen_out) {
+    const FrameJob& J = jobs[blockIdx.y];
     __shared__ uint32_t s_warp[33];
-    if (J.l == 0) { if (threadIdx.x == 0) wlen_out[blockIdx.x] = 0; return; }
+    if (J.l == 0) { if (threadIdx.x == 0 && blockIdx.x == 0) wlen_out[blockIdx.y] = 0; return; }
     const uint32_t ncent = (J.n + 99u) / 100u;
+    const uint32_t c0 = (uint32_t)(((uint64_t)ncent * blockIdx.x) / chunks), c1 = (uint32_t)(((uint64_t)ncent * (blockIdx.x + 1)) / chunks);
     const uint4* pass4 = reinterpret_cast<const uint4*>(J.pass);
     uint32_t base = 0;
-    for (uint32_t r0 = 0; r0 < ncent; r0 += blockDim.x) {
+    for (uint32_t i = 0; i < blockIdx.x; i++) base += counts[blockIdx.y * chunks + i];   // passes before this chunk
+    for (uint32_t r0 = c0; r0 < c1; r0 += blockDim.x) {
         const uint32_t c = r0 + threadIdx.x;
         uint64_t wlo = 0, whi = 0;
         uint32_t cnt = 0;
-        if (c < ncent) {
+        if (c < c1) {
             const uint4 p = pass4[c];
             const Bits128 mb = load_bits100(J.mask, c, min(100u, J.n - 100u * c));
             const uint32_t P[4] = {p.x, p.y, p.z, p.w};
@@ -1175,31 +1204,37 @@ __global__ void __launch_bounds__(1024) k_witness(const FrameJob* __restrict__ j
         if (cnt) or_bits128(J.witness, (uint64_t)base + off, wlo, whi);
         base += tot;
     }
-    __threadfence();                                    // the RED.ORs above must be performed before the in-place pass below
-    __syncthreads();
-    const uint32_t wwords = (base + 31u) >> 5;
-    for (uint32_t i = threadIdx.x; i < wwords; i += blockDim.x) J.witness[i] = bitrev_bytes(__ldcg(J.witness + i));
-    const uint32_t bwords = (J.l + 31u) >> 5;
-    for (uint32_t i = threadIdx.x; i < bwords; i += blockDim.x) J.bits[i] = bitrev_bytes(__ldcg(J.bits + i));
-    if (threadIdx.x == 0) wlen_out[blockIdx.x] = base;
+    if (threadIdx.x == 0 && blockIdx.x == chunks - 1) wlen_out[blockIdx.y] = base;
+}
+
+// witness and bit array: LSB-first words -> np.packbits order, in place (ivc:945, ivc:951)
+__global__ void __launch_bounds__(256) k_finalize(const FrameJob* __restrict__ jobs, const uint32_t* __restrict__ wlen) {
+    const FrameJob& J = jobs[blockIdx.y];
+    if (J.l == 0) return;
+    const uint32_t wwords = (wlen[blockIdx.y] + 31u) >> 5, bwords = (J.l + 31u) >> 5;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < wwords; i += gridDim.x * blockDim.x) J.witness[i] = bitrev_bytes(J.witness[i]);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < bwords; i += gridDim.x * blockDim.x) J.bits[i] = bitrev_bytes(J.bits[i]);
 }
 
 // ------------------------------------------------------------------------------------------
 // K4b: decode expand.  out[i] = witness[rank of i among passing positions] (ivc:299-304).
 // Witness here is LSB-first (the host converts the packbits input once with k_bitrev).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_expand(const FrameJob* __restrict__ jobs, uint32_t* __restrict__ consumed) {
-    const FrameJob& J = jobs[blockIdx.x];
+__global__ void __launch_bounds__(1024) k_expand(const FrameJob* __restrict__ jobs, uint32_t chunks, const uint32_t* __restrict__ counts,
+                                                 uint32_t* __restrict__ consumed) {
+    const FrameJob& J = jobs[blockIdx.y];
     __shared__ uint32_t s_warp[33];
-    if (J.l == 0) { if (threadIdx.x == 0) consumed[blockIdx.x] = 0; return; }
+    if (J.l == 0) { if (threadIdx.x == 0 && blockIdx.x == 0) consumed[blockIdx.y] = 0; return; }
     const uint32_t ncent = (J.n + 99u) / 100u;
+    const uint32_t c0 = (uint32_t)(((uint64_t)ncent * blockIdx.x) / chunks), c1 = (uint32_t)(((uint64_t)ncent * (blockIdx.x + 1)) / chunks);
     const uint4* pass4 = reinterpret_cast<const uint4*>(J.pass);
     uint32_t base = 0;
-    for (uint32_t r0 = 0; r0 < ncent; r0 += blockDim.x) {
+    for (uint32_t i = 0; i < blockIdx.x; i++) base += counts[blockIdx.y * chunks + i];
+    for (uint32_t r0 = c0; r0 < c1; r0 += blockDim.x) {
         const uint32_t c = r0 + threadIdx.x;
         uint4 p = make_uint4(0, 0, 0, 0);
         uint32_t cnt = 0;
-        if (c < ncent) { p = pass4[c]; cnt = __popc(p.x) + __popc(p.y) + __popc(p.z) + __popc(p.w); }
+        if (c < c1) { p = pass4[c]; cnt = __popc(p.x) + __popc(p.y) + __popc(p.z) + __popc(p.w); }
         uint32_t tot;
         const uint32_t off = base + block_excl_scan(cnt, s_warp, tot);
         if (cnt) {
@@ -1233,7 +1268,7 @@ __global__ void __launch_bounds__(1024) k_expand(const FrameJob* __restrict__ jo
         }
         base += tot;
     }
-    if (threadIdx.x == 0) consumed[blockIdx.x] = base;
+    if (threadIdx.x == 0 && blockIdx.x == chunks - 1) consumed[blockIdx.y] = base;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1516,14 +1551,30 @@ cudaError_t launch_query(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_witness(const FrameJob* d_jobs, int F, uint32_t* d_wlen, cudaStream_t st) {
+static uint32_t witness_chunks(int F, uint32_t max_centuries, int sm_count) {
+    uint32_t ch = (uint32_t)((4 * sm_count + F - 1) / F);             // aim at ~4 CTAs per SM (two resident at a time)
+    const uint32_t by_size = max_centuries / 4096u;                   // at least 4096 centuries (4 rounds) per chunk
+    if (ch > by_size) ch = by_size;
+    if (ch > 32u) ch = 32u;
+    if (ch < 1u) ch = 1u;
+    return ch;
+}
+// K3b: d_scratch holds F*32 uint32 (pass counts per chunk)
+cudaError_t launch_witness(const FrameJob* d_jobs, int F, uint32_t max_centuries, int sm_count, uint32_t* d_scratch, uint32_t* d_wlen,
+                           cudaStream_t st) {
     if (F <= 0) return cudaSuccess;
-    k_witness<<<F, 1024, 0, st>>>(d_jobs, d_wlen);
+    const uint32_t ch = witness_chunks(F, max_centuries, sm_count);
+    if (ch > 1u) k_pass_count<<<dim3(ch, (unsigned)F), 256, 0, st>>>(d_jobs, ch, d_scratch);
+    k_witness<<<dim3(ch, (unsigned)F), 1024, 0, st>>>(d_jobs, ch, d_scratch, d_wlen);
+    k_finalize<<<dim3(8, (unsigned)F), 256, 0, st>>>(d_jobs, d_wlen);
     return cudaGetLastError();
 }
-cudaError_t launch_expand(const FrameJob* d_jobs, int F, uint32_t* d_consumed, cudaStream_t st) {
+cudaError_t launch_expand(const FrameJob* d_jobs, int F, uint32_t max_centuries, int sm_count, uint32_t* d_scratch, uint32_t* d_consumed,
+                          cudaStream_t st) {
     if (F <= 0) return cudaSuccess;
-    k_expand<<<F, 1024, 0, st>>>(d_jobs, d_consumed);
+    const uint32_t ch = witness_chunks(F, max_centuries, sm_count);
+    if (ch > 1u) k_pass_count<<<dim3(ch, (unsigned)F), 256, 0, st>>>(d_jobs, ch, d_scratch);
+    k_expand<<<dim3(ch, (unsigned)F), 1024, 0, st>>>(d_jobs, ch, d_scratch, d_consumed);
     return cudaGetLastError();
 }
 static inline unsigned grid_for(size_t n, unsigned block) {

@@ -53,8 +53,10 @@ cudaError_t launch_threshold(const PairJob* d_pairs, int F, uint32_t npix, int c
 cudaError_t launch_insert(const FrameJob* d_jobs, int F, uint32_t max_centuries, int variant, int sm_count, cudaStream_t st);
 cudaError_t launch_query(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, int F, uint32_t total_centuries,
                          uint32_t max_l_bits, int variant, int sm_count, int smem_bytes_cap, cudaStream_t st);
-cudaError_t launch_witness(const FrameJob* d_jobs, int F, uint32_t* d_wlen, cudaStream_t st);
-cudaError_t launch_expand(const FrameJob* d_jobs, int F, uint32_t* d_consumed, cudaStream_t st);
+cudaError_t launch_witness(const FrameJob* d_jobs, int F, uint32_t max_centuries, int sm_count, uint32_t* d_scratch, uint32_t* d_wlen,
+                           cudaStream_t st);
+cudaError_t launch_expand(const FrameJob* d_jobs, int F, uint32_t max_centuries, int sm_count, uint32_t* d_scratch, uint32_t* d_consumed,
+                          cudaStream_t st);
 cudaError_t launch_gather_scatter(const GatherJob* d_jobs, int F, int scatter, uint32_t* d_counts, cudaStream_t st);
 cudaError_t launch_bitrev(uint32_t* d_words, size_t nwords, cudaStream_t st);
 cudaError_t launch_unpack_bits(const uint32_t* d_words, uint8_t* d_out, size_t nbits, cudaStream_t st);
