@@ -172,6 +172,10 @@ int rbf_stream_gather_changed(rbf_stream* s, uint32_t pairs, uint8_t* values_out
 int rbf_stream_apply_diff(rbf_stream* s, uint32_t base_frame, uint32_t out_frame, const uint8_t* mask_packed_little,
                           const uint8_t* values, uint64_t values_bytes, uint64_t* applied_pixels);
 int rbf_stream_download(rbf_stream* s, uint32_t frame, void* host_out);
+/* N3  the 5x5 median of cv2.medianBlur in VideoFrameCompressor._estimate_noise_level (ivc:738): replicated border, 13th
+ *     smallest of 25, exact for uint8 / uint16.  The float32 std of (frame - median) stays in numpy (ivc:741-744). */
+int rbf_median_blur5(rbf_ctx* ctx, const void* plane_in, uint32_t height, uint32_t width, uint32_t sample_bytes, void* plane_out);
+int rbf_stream_median5(rbf_stream* s, uint32_t frame, void* plane_out);   /* channel 0 of a resident frame */
 
 /* ------------------------------------------------------------------ multi-GPU (one process per GPU)
  * frames are sharded across ranks; the per-rank Bloom bit arrays are exchanged with ONE ncclAllGather

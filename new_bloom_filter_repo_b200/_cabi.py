@@ -47,7 +47,7 @@ EXPORTS = [
     "rbf_compress_mask", "rbf_decompress_mask",
     "rbf_stream_create", "rbf_stream_destroy", "rbf_stream_upload", "rbf_stream_frame_ptr", "rbf_stream_encode",
     "rbf_stream_encode_host", "rbf_stream_fetch", "rbf_stream_decode_verify", "rbf_stream_bitmap_region", "rbf_stream_stage_ms",
-    "rbf_stream_gather_changed", "rbf_stream_apply_diff", "rbf_stream_download",
+    "rbf_stream_gather_changed", "rbf_stream_apply_diff", "rbf_stream_download", "rbf_median_blur5", "rbf_stream_median5",
     "rbf_nccl_unique_id", "rbf_nccl_init", "rbf_nccl_allgather", "rbf_stream_allgather_bitmaps", "rbf_nccl_destroy",
 ]
 
@@ -113,6 +113,8 @@ def _sig(L):
     L.rbf_stream_gather_changed.argtypes = [vp, u32, vp, u64, vp]
     L.rbf_stream_apply_diff.argtypes = [vp, u32, u32, vp, vp, u64, P(u64)]
     L.rbf_stream_download.argtypes = [vp, u32, vp]
+    L.rbf_median_blur5.argtypes = [vp, vp, u32, u32, u32, vp]
+    L.rbf_stream_median5.argtypes = [vp, u32, vp]
     L.rbf_nccl_unique_id.argtypes = [vp]
     L.rbf_nccl_init.argtypes = [vp, vp, i32, i32]
     L.rbf_nccl_allgather.argtypes = [vp, vp, vp, u64]

@@ -938,6 +938,39 @@ extern "C" int rbf_stream_download(rbf_stream* s, uint32_t frame, void* host_out
     return RBF_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// N3: cv2.medianBlur(frame, 5) of VideoFrameCompressor._estimate_noise_level (ivc:738)
+// ------------------------------------------------------------------------------------------
+extern "C" int rbf_median_blur5(rbf_ctx* c, const void* plane_in, uint32_t H, uint32_t W, uint32_t sample_bytes, void* plane_out) {
+    if (!c || !plane_in || !plane_out) return set_err(c, RBF_ERR_INVALID, "rbf_median_blur5: NULL");
+    if (!(sample_bytes == 1 || sample_bytes == 2) || H == 0 || W == 0) return set_err(c, RBF_ERR_INVALID, "rbf_median_blur5: bad shape");
+    CK(c, cudaSetDevice(c->device));
+    const size_t bytes = (size_t)H * W * sample_bytes;
+    void *d_in, *d_out;
+    int rc;
+    if ((rc = scratch_get(c, 11, bytes, &d_in)) || (rc = scratch_get(c, 12, bytes, &d_out))) return rc;
+    CK(c, cudaMemcpyAsync(d_in, plane_in, bytes, cudaMemcpyHostToDevice, c->st)); c->h2d += (int64_t)bytes;
+    LAUNCH(c, launch_median5(d_in, 1, H, W, (int)sample_bytes, d_out, c->st));
+    CK(c, cudaMemcpyAsync(plane_out, d_out, bytes, cudaMemcpyDeviceToHost, c->st)); c->d2h += (int64_t)bytes;
+    CK(c, cudaStreamSynchronize(c->st));
+    return RBF_OK;
+}
+
+extern "C" int rbf_stream_median5(rbf_stream* s, uint32_t frame, void* plane_out) {
+    if (!s || !plane_out || frame >= s->max_frames) return set_err(s ? s->c : nullptr, RBF_ERR_INVALID, "rbf_stream_median5: bad argument");
+    rbf_ctx* c = s->c;
+    CK(c, cudaSetDevice(c->device));
+    const size_t bytes = (size_t)s->npix * s->S;
+    void* d_out;
+    int rc;
+    if ((rc = scratch_get(c, 12, bytes, &d_out))) return rc;
+    LAUNCH(c, launch_median5(s->d_frames + (size_t)frame * s->frame_stride, s->C, s->H, s->W, (int)s->S, d_out, c->st));
+    CK(c, cudaMemcpyAsync(plane_out, d_out, bytes, cudaMemcpyDeviceToHost, c->st)); c->d2h += (int64_t)bytes;
+    CK(c, cudaStreamSynchronize(c->st));
+    return RBF_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // NCCL (dlopen'ed so that single-GPU use needs no NCCL at all)
 // ------------------------------------------------------------------------------------------

@@ -1305,6 +1305,38 @@ __global__ void __launch_bounds__(1024) k_gather_scatter(const GatherJob* __rest
 }
 
 // ------------------------------------------------------------------------------------------
+// N3: the 5x5 median of cv2.medianBlur (ivc:738) -- replicated border, 13th smallest of
+// the 25 samples -- on channel 0 of an interleaved frame.  Rank selection (25 x 25 comparisons) is
+// exact for any sample type; the float32 std that follows (ivc:741-744) stays in numpy on the host so
+// that the noise estimate is bit-identical to the reference's.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_median5(const T* __restrict__ in, uint32_t pix_stride, uint32_t H, uint32_t W,
+                                                  T* __restrict__ out) {
+    const uint32_t x = blockIdx.x * 32u + (threadIdx.x & 31u), y = blockIdx.y * 8u + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    uint32_t v[25];
+#pragma unroll
+    for (int dy = -2; dy <= 2; dy++) {
+        const uint32_t yy = (uint32_t)min(max((int)y + dy, 0), (int)H - 1);
+#pragma unroll
+        for (int dx = -2; dx <= 2; dx++) {
+            const uint32_t xx = (uint32_t)min(max((int)x + dx, 0), (int)W - 1);
+            v[(dy + 2) * 5 + (dx + 2)] = (uint32_t)__ldg(in + ((size_t)yy * W + xx) * pix_stride);
+        }
+    }
+    uint32_t med = 0;
+#pragma unroll
+    for (int i = 0; i < 25; i++) {
+        uint32_t rank = 0;
+#pragma unroll
+        for (int j = 0; j < 25; j++) rank += (v[j] < v[i] || (v[j] == v[i] && j < i)) ? 1u : 0u;
+        if (rank == 12u) med = v[i];
+    }
+    out[(size_t)y * W + x] = (T)med;
+}
+
+// ------------------------------------------------------------------------------------------
 // small utilities
 // ------------------------------------------------------------------------------------------
 __global__ void k_bitrev(uint32_t* __restrict__ w, size_t n) {
@@ -1586,6 +1618,14 @@ static inline unsigned grid_for(size_t n, unsigned block) {
 cudaError_t launch_gather_scatter(const GatherJob* d_jobs, int F, int scatter, uint32_t* d_counts, cudaStream_t st) {
     if (F <= 0) return cudaSuccess;
     k_gather_scatter<<<F, 1024, 0, st>>>(d_jobs, scatter, d_counts);
+    return cudaGetLastError();
+}
+cudaError_t launch_median5(const void* d_in, uint32_t pix_stride, uint32_t H, uint32_t W, int sample_bytes, void* d_out, cudaStream_t st) {
+    if (H == 0 || W == 0) return cudaSuccess;
+    dim3 grid((W + 31u) / 32u, (H + 7u) / 8u);
+    if (sample_bytes == 1) k_median5<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)d_in, pix_stride, H, W, (uint8_t*)d_out);
+    else if (sample_bytes == 2) k_median5<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)d_in, pix_stride, H, W, (uint16_t*)d_out);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 cudaError_t launch_bitrev(uint32_t* d_words, size_t nwords, cudaStream_t st) {

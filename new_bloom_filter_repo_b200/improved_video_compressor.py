@@ -169,6 +169,22 @@ class VideoFrameCompressor:
         self.bloom_compressor = BloomFilterCompressor(verbose=False)   # the attribute ivc:927 needs
         self._streams: Dict[tuple, FrameStream] = {}
 
+    def _estimate_noise_level(self, frame: np.ndarray) -> float:                  # ivc:727-746
+        """N3: the 5x5 median runs on the device (k_median5, bit-exact with cv2.medianBlur); the float32 std is numpy's,
+        exactly as in the reference."""
+        a = np.ascontiguousarray(_frame_data(frame))
+        if a.ndim != 2 or a.dtype not in (np.uint8, np.uint16):
+            raise NotImplementedError("noise estimate is implemented for 2-D uint8/uint16 planes (the Y / gray plane)")
+        smoothed = np.empty_like(a)
+        _cabi.check(_cabi.lib().rbf_median_blur5(_cabi.ctx(), _cabi.ptr(a), a.shape[0], a.shape[1], a.dtype.itemsize,
+                                                 _cabi.ptr(smoothed)), _cabi.ctx())
+        noise = a.astype(np.float32) - smoothed.astype(np.float32)                 # ivc:741
+        return np.std(noise)                                                       # ivc:744
+
+    def _adaptive_diff_threshold(self, frame: np.ndarray) -> float:               # ivc:748-766
+        noise_level = self._estimate_noise_level(frame)
+        return max(self.min_diff_threshold, min(self.max_diff_threshold, noise_level * self.noise_tolerance))
+
     def _stream_for(self, shape, dtype) -> FrameStream:
         key = (tuple(shape), np.dtype(dtype).str)
         s = self._streams.get(key)
@@ -186,9 +202,8 @@ class VideoFrameCompressor:
         if is_color and not (self.use_direct_yuv and pd.shape[2] >= 3):
             raise NotImplementedError("BGR->gray masks (ivc:794-795) are outside the accelerated path; pass YUV frames "
                                       "with use_direct_yuv=True")
-        if threshold is None:
-            raise NotImplementedError("adaptive threshold (cv2.medianBlur noise estimate, ivc:727-766) is the N3 row of "
-                                      "SURVEY.md section 8f; pass threshold= explicitly")
+        if threshold is None:                                  # ivc:804-805: adaptive threshold from the current Y / gray plane
+            threshold = self._adaptive_diff_threshold(cd[:, :, 0].copy() if is_color else cd.copy())
         if pd.dtype not in (np.uint8, np.uint16) or pd.shape != cd.shape or pd.dtype != cd.dtype:
             raise ValueError("frames must be equal-shape uint8/uint16 arrays")
         st = self._stream_for(pd.shape, pd.dtype)

@@ -333,6 +333,36 @@ def gen_keyframes():
     np.savez_compressed(os.path.join(HERE, "keyframe_arrays.npz"), **arrays)
 
 
+# ---------------------------------------------------------------- adaptive threshold (ivc:727-766), SURVEY 8f N3
+def gen_adaptive():
+    recs = []
+    for name, h, w, seed, pc, dt, noise_amp in [("u8_smooth", 72, 96, 61, 0.05, np.uint8, 2), ("u8_noisy", 72, 96, 62, 0.05, np.uint8, 40),
+                                                  ("u8_edge", 7, 9, 63, 0.3, np.uint8, 10), ("u16", 40, 56, 64, 0.05, np.uint16, 300),
+                                                  ("u8_tiny", 64, 80, 65, 0.002, np.uint8, 1), ("u8_mid", 64, 80, 66, 0.004, np.uint8, 2)]:
+        rng = np.random.default_rng(seed)
+        hi = 256 if dt == np.uint8 else 65536
+        yy, xx = np.mgrid[0:h, 0:w]
+        base = ((yy * 5 + xx * 3) * (hi // 512) % (hi - 2 * noise_amp - 1)).astype(np.int64)
+        if name in ("u8_tiny", "u8_mid"):
+            base = ((yy + xx) // 4 + 20).astype(np.int64)      # no wrap edges: the noise estimate stays below the clamp
+        prev = np.stack([base + rng.integers(0, noise_amp + 1, (h, w)) for _ in range(3)], axis=-1).astype(dt)
+        curr = prev.copy()
+        ch = rng.random((h, w)) < pc
+        delta = {"u8_tiny": 20, "u8_mid": 30}.get(name, hi // 4)
+        curr[ch] = (curr[ch].astype(np.int64) + delta) % hi
+        vfc = refshim.make_vfc(ivc, use_direct_yuv=True)
+        y = curr[:, :, 0].copy()
+        nl = vfc._estimate_noise_level(y)
+        thr = vfc._adaptive_diff_threshold(y)
+        mask, changed, dens = vfc._calculate_frame_diff(vfc_wrap(prev), vfc_wrap(curr), threshold=None)
+        import cv2
+        recs.append({"name": name, "h": h, "w": w, "seed": seed, "p_change": pc, "dtype": np.dtype(dt).name, "noise_amp": noise_amp, "delta": int(delta),
+                     "noise_level": float(nl).hex(), "noise_level_type": type(nl).__name__, "threshold": float(thr).hex(),
+                     "median_sha256": sha(cv2.medianBlur(y, 5)), "ones": int(mask.sum()), "mask_sha256": sha(np.packbits(mask.reshape(-1)))})
+        print(name, nl, thr, int(mask.sum()))
+    dump("adaptive_kat.json", {"cases": recs})
+
+
 if __name__ == "__main__":
     gen_xxh64()
     gen_filter()
@@ -342,3 +372,4 @@ if __name__ == "__main__":
     gen_frames()
     gen_strings()
     gen_keyframes()
+    gen_adaptive()

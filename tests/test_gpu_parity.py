@@ -452,3 +452,44 @@ def test_compress_empty_and_constant_inputs(pkg):
     assert bitmap is ones and witness == [] and p == 1.0 and ratio == 1.0
     with pytest.raises(ValueError):
         comp.compress(np.full(10, 2, dtype=np.uint8))            # not a 0/1 vector
+
+
+# ------------------------------------------------------------------ adaptive threshold (ivc:727-766)
+def test_adaptive_threshold_against_golden(pkg):
+    import hashlib
+    g = golden_json("adaptive_kat.json")
+    vfc = pkg.VideoFrameCompressor(use_direct_yuv=True)
+    for rec in g["cases"]:
+        dt = np.dtype(rec["dtype"]).type
+        h, w, noise_amp = rec["h"], rec["w"], rec["noise_amp"]
+        rng = np.random.default_rng(rec["seed"])
+        hi = 256 if dt == np.uint8 else 65536
+        yy, xx = np.mgrid[0:h, 0:w]
+        base = ((yy * 5 + xx * 3) * (hi // 512) % (hi - 2 * noise_amp - 1)).astype(np.int64)
+        if rec["name"] in ("u8_tiny", "u8_mid"):
+            base = ((yy + xx) // 4 + 20).astype(np.int64)
+        prev = np.stack([base + rng.integers(0, noise_amp + 1, (h, w)) for _ in range(3)], axis=-1).astype(dt)
+        curr = prev.copy()
+        ch = rng.random((h, w)) < rec["p_change"]
+        curr[ch] = (curr[ch].astype(np.int64) + rec["delta"]) % hi
+        y = curr[:, :, 0].copy()
+        smoothed = np.empty_like(y)
+        pkg._cabi.check(pkg._cabi.lib().rbf_median_blur5(pkg._cabi.ctx(), pkg._cabi.ptr(y), h, w, y.dtype.itemsize, pkg._cabi.ptr(smoothed)), pkg._cabi.ctx())
+        assert sha(smoothed) == rec["median_sha256"], rec["name"]          # == cv2.medianBlur(y, 5)
+        nl = vfc._estimate_noise_level(y)
+        assert type(nl).__name__ == rec["noise_level_type"] and float(nl).hex() == rec["noise_level"], rec["name"]
+        assert float(vfc._adaptive_diff_threshold(y)).hex() == rec["threshold"]
+        mask, changed, dens = vfc._calculate_frame_diff(pkg.YUVFrame(prev), pkg.YUVFrame(curr), threshold=None)
+        assert int(mask.sum()) == rec["ones"] and sha(np.packbits(mask.reshape(-1))) == rec["mask_sha256"], rec["name"]
+
+
+def test_median5_resident_frame_matches_cv2(pkg):
+    cv2 = pytest.importorskip("cv2")
+    import ctypes as C
+    frames = synth_stream(270, 481, 2, 8, [0.1])
+    st = pkg.FrameStream(270, 481, 3, np.uint8, max_frames=2)
+    st.upload(frames)
+    out = np.empty((270, 481), np.uint8)
+    pkg._cabi.check(pkg._cabi.lib().rbf_stream_median5(st._h, 1, pkg._cabi.ptr(out)), pkg._cabi.ctx())
+    assert np.array_equal(out, cv2.medianBlur(np.ascontiguousarray(frames[1][:, :, 0]), 5))
+    st.close()
