@@ -39,8 +39,6 @@ struct rbf_ctx {
     int64_t launches = 0, h2d = 0, d2h = 0;
     std::vector<void*> scratch;
     std::vector<size_t> scratch_sz;
-    void* pinned = nullptr;
-    size_t pinned_sz = 0;
     // NCCL (dlopen'ed)
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;
@@ -84,18 +82,6 @@ static int scratch_get(rbf_ctx* c, int slot, size_t bytes, void** out) {
     *out = c->scratch[slot];
     return RBF_OK;
 }
-static int pinned_get(rbf_ctx* c, size_t bytes, void** out) {
-    if (c->pinned_sz < bytes) {
-        if (c->pinned) CK(c, cudaFreeHost(c->pinned));
-        c->pinned = nullptr; c->pinned_sz = 0;
-        size_t nb = align_up(bytes * 2, 4096);
-        CK(c, cudaMallocHost(&c->pinned, nb));
-        c->pinned_sz = nb;
-    }
-    *out = c->pinned;
-    return RBF_OK;
-}
-
 // ------------------------------------------------------------------------------------------
 // exact host-side scalars
 // ------------------------------------------------------------------------------------------
@@ -224,7 +210,6 @@ extern "C" void rbf_ctx_destroy(rbf_ctx* c) {
     cudaSetDevice(c->device);
     rbf_nccl_destroy(c);
     for (void* p : c->scratch) if (p) cudaFree(p);
-    if (c->pinned) cudaFreeHost(c->pinned);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->st) cudaStreamDestroy(c->st);
