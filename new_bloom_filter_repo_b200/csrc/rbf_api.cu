@@ -231,7 +231,7 @@ extern "C" int rbf_device_info(rbf_ctx* c, char* name, int name_len, int* sm_cou
 extern "C" int rbf_set_option(rbf_ctx* c, const char* key, int64_t v) {
     if (!c || !key) return set_err(c, RBF_ERR_INVALID, "rbf_set_option: NULL");
     if (!strcmp(key, "k1_variant")) { c->k1_variant = (int)v; return RBF_OK; }
-    if (!strcmp(key, "query_variant")) { c->query_variant = (int)(v < 0 ? 0 : (v > 3 ? 3 : v)); return RBF_OK; }
+    if (!strcmp(key, "query_variant")) { c->query_variant = (int)(v < 0 ? 0 : (v > 4 ? 4 : v)); return RBF_OK; }
     if (!strcmp(key, "insert_variant")) { c->insert_variant = v ? 1 : 0; return RBF_OK; }
     if (!strcmp(key, "host_chunk_frames")) { c->host_chunk_frames = (int)v; return RBF_OK; }
     if (!strcmp(key, "k1_only")) { c->k1_only = v ? 1 : 0; return RBF_OK; }

@@ -696,7 +696,9 @@ __device__ __forceinline__ uint32_t probe_bit(uint32_t sm_addr, uint32_t sm_addr
     const uint32_t w = idx >> 5;
     uint32_t word;
     if (PM == 1) {
-        asm("{\n .reg .pred q;\n setp.lt.u32 q, %1, %2;\n @q ld.shared.u32 %0, [%3];\n @!q ld.global.nc.u32 %0, [%4];\n}"
+        // the unconditional mov makes the two predicated loads a full definition for ptxas (otherwise `word` stays live
+        // across loop iterations and is spilled right behind the load, stalling on it)
+        asm("{\n .reg .pred q;\n setp.lt.u32 q, %1, %2;\n mov.u32 %0, 0;\n @q ld.shared.u32 %0, [%3];\n @!q ld.global.nc.u32 %0, [%4];\n}"
             : "=r"(word)
             : "r"(w), "r"(sm_words), "r"(sm_addr + 4u * w), "l"(gl + w));
     } else if (PM == 2) {
@@ -942,6 +944,220 @@ __device__ __noinline__ void query_slab_dense(const FilterK K, uint32_t sm_addr,
         pass4[c] = acc;
     }
     __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 (decade tiles): compaction without a per-position ring push.  A warp evaluates stage A for a
+// whole decade -- ten positions per lane, y a compile-time constant, ten independent XXH64 chains
+// per lane (ILP) -- then ONE warp scan of the survivor counts places every survivor in a flat
+// per-decade buffer of 4-byte records {idx0:23, lane:5, y:4}.  Stage B consumes the buffer in dense
+// batches of 32 and fetches the owner's decade state of seed 2 with a shuffle (all records of the
+// buffer belong to the current decade).  Survivors of B go through the small stage-C ring as before.
+// Requires m <= 2^23 (4K and 8K frames); larger filters use the ring kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int Q3_BUF = 320;                                          // survivors of one decade of a slab, worst case
+constexpr int Q3_WARP_WORDS = Q3_BUF + (Q2_RING * 8 + 32 * 16 + 128) / 4;   // decade buffer, C ring, pass accumulators, digit table
+
+__device__ __forceinline__ void sts32_if(uint32_t addr, uint32_t v, bool p) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.shared.u32 [%0], %1;\n}" ::"r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+template <int KIND, int PM>
+__device__ __forceinline__ void drain_c_ring(const FilterK& K, uint32_t sm_addr, uint32_t sm_addr1, const uint32_t* __restrict__ gl,
+                                             uint32_t sm_words, uint32_t qc_addr, uint32_t pacc_addr, uint32_t lane, uint64_t CA,
+                                             uint32_t& qc_head, uint32_t& qc_cnt) {
+    __syncwarp();
+    const uint32_t nc = min(32u, qc_cnt);
+    const bool have = lane < nc;
+    const uint2 r = lds64(qc_addr + 8u * ((qc_head + lane) & (Q2_RING - 1)));
+    qc_head = (qc_head + nc) & (Q2_RING - 1);
+    qc_cnt -= nc;
+    const uint32_t tag = have ? r.y : 0u;
+    const uint32_t owner = (tag >> 8) & 31u;
+    const uint64_t CAo = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)CA, owner) |
+                         ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(CA >> 32), owner) << 32);
+    const uint64_t hA = finish_t<KIND>(decade_state_t<KIND>(CAo, K.sA, (tag >> 4) & 15u), K.sA, tag & 15u);
+    const uint32_t pb = probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, have ? r.x : 0u);
+    deliver_pass(pacc_addr, tag, have && (!(hA < K.T) || pb != 0u));
+}
+
+template <int KIND, int FKT, int PM>
+__device__ __noinline__ void query_slab_tiled(const FilterK K, uint32_t sm_addr, uint32_t sm_addr1,
+                                              const uint32_t* __restrict__ gl, uint32_t sm_words,
+                                              const uint32_t* __restrict__ mask, uint32_t n, uint32_t slab_c0,
+                                              uint32_t c_end, uint4* __restrict__ pass4, uint32_t buf_addr) {
+    const uint32_t qc_addr = buf_addr + 4u * Q3_BUF, pacc_addr = qc_addr + 8u * Q2_RING, rb_addr = pacc_addr + 512u;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t c = slab_c0 + lane;
+    const bool active = c < c_end;
+    const Century cen = make_century(active ? c : slab_c0);
+    const uint64_t C1 = century_state(cen, K.s1), C2 = century_state(cen, K.s2), CA = century_state(cen, K.sA);
+    const uint32_t nvalid = active ? min(100u, n - 100u * c) : 0u;
+    uint64_t skip_lo = 0, skip_hi = 0;                               // known members and positions beyond n need no hashing
+    if (active && mask != nullptr) { const Bits128 mb = load_bits100(mask, c, nvalid); skip_lo = mb.lo; skip_hi = mb.hi; }
+    if (nvalid < 64u) { skip_hi = ~0ull; skip_lo |= ~((1ull << nvalid) - 1ull); }
+    else skip_hi |= ~((1ull << (nvalid - 64u)) - 1ull);
+    if (lane < 10u) sts64_if(rb_addr + 8u * lane, (uint32_t)c_rot_digit[lane], (uint32_t)(c_rot_digit[lane] >> 32), true);
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t qc_head = 0, qc_cnt = 0;
+#pragma unroll 1
+    for (uint32_t x = 0; x < 10u; x++) {
+        const uint64_t D1 = decade_prep<KIND>(decade_state_t<KIND>(C1, K.s1, x));
+        const uint64_t D2 = decade_prep<KIND>(decade_state_t<KIND>(C2, K.s2, x));
+        const uint32_t p0 = 10u * x;
+        const uint64_t sh = (p0 < 64u) ? ((skip_lo >> p0) | (p0 ? (skip_hi << (64u - p0)) : 0ull)) : (skip_hi >> (p0 - 64u));
+        // ---- stage A: ten positions per lane, y compile-time
+        uint32_t idx0[10];
+        uint32_t sv = 0;
+#pragma unroll
+        for (int y = 0; y < 10; y++) {
+            idx0[y] = mod_fast(finish_prep<KIND>(D1, K.s1, (uint32_t)y, rot_digit_const((uint32_t)y)), K.fm);
+            sv |= probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx0[y]) << y;
+        }
+        sv &= ~(uint32_t)sh & 0x3ffu;
+        // ---- one scan per decade places the survivors
+        const uint32_t cnt = __popc(sv);
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (uint32_t)d) inc += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        uint32_t off = buf_addr + 4u * (inc - cnt);
+        const uint32_t ltag = lane << 23;
+#pragma unroll
+        for (int y = 0; y < 10; y++) {
+            const bool p = ((sv >> y) & 1u) != 0u;
+            sts32_if(off, idx0[y] | ltag | ((uint32_t)y << 28), p);
+            off += p ? 4u : 0u;
+        }
+        __syncwarp();
+        // ---- stage B: dense batches of 32 survivors of this decade
+#pragma unroll 1
+        for (uint32_t b = 0; b < total; b += 32u) {
+            const uint32_t g = b + lane;
+            const bool have = g < total;
+            const uint32_t rec = lds32(buf_addr + 4u * min(g, (uint32_t)(Q3_BUF - 1)));
+            const uint32_t owner = (rec >> 23) & 31u, y = have ? (rec >> 28) : 0u;
+            const uint64_t D2o = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)D2, owner) |
+                                 ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(D2 >> 32), owner) << 32);
+            uint64_t rb = 0;
+            if (kind_ends_in_byte<KIND>()) { const uint2 t = lds64(rb_addr + 8u * y); rb = (uint64_t)t.x | ((uint64_t)t.y << 32); }
+            const uint32_t stepm = have ? mod_fast(finish_prep<KIND>(D2o, K.s2, y, rb), K.fm) : 0u;
+            uint32_t idx = have ? (rec & 0x7fffffu) : 0u;
+            uint32_t ok = have ? 1u : 0u;
+            if (FKT > 0) {
+#pragma unroll
+                for (int i = 1; i < FKT; i++) {
+                    idx = addmod_fast(idx, stepm, K.fm.m);
+                    ok &= probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx);
+                }
+            } else {
+                for (uint32_t i = 1; i < K.fk; i++) {
+                    idx = addmod_fast(idx, stepm, K.fm.m);
+                    ok &= probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx);
+                }
+            }
+            const uint32_t tag = (owner << 8) | (x << 4) | y;
+            if (K.has_act) {
+                idx = addmod_fast(idx, stepm, K.fm.m);               // index of probe floor_k
+                const uint32_t b2 = __ballot_sync(0xffffffffu, ok != 0u);
+                sts64_if(qc_addr + 8u * ((qc_head + qc_cnt + __popc(b2 & lt)) & (Q2_RING - 1)), idx, tag, ok != 0u);
+                qc_cnt += __popc(b2);
+                if (qc_cnt >= 32u) drain_c_ring<KIND, PM>(K, sm_addr, sm_addr1, gl, sm_words, qc_addr, pacc_addr, lane, CA, qc_head, qc_cnt);
+            } else {
+                deliver_pass(pacc_addr, tag, ok != 0u);
+            }
+        }
+        __syncwarp();                                                // the decade buffer is rewritten next
+    }
+#pragma unroll 1
+    while (qc_cnt) drain_c_ring<KIND, PM>(K, sm_addr, sm_addr1, gl, sm_words, qc_addr, pacc_addr, lane, CA, qc_head, qc_cnt);
+    __syncwarp();
+    uint4 acc = lds128(pacc_addr + 16u * lane);
+    sts128_if(pacc_addr + 16u * lane, 0u, 0u, 0u, 0u, true);
+    if (active) {
+        if (mask != nullptr) {                                       // known members pass (no false negatives)
+            const Bits128 mb = load_bits100(mask, c, nvalid);
+            acc.x |= (uint32_t)mb.lo; acc.y |= (uint32_t)(mb.lo >> 32); acc.z |= (uint32_t)mb.hi; acc.w |= (uint32_t)(mb.hi >> 32);
+        }
+        pass4[c] = acc;
+    }
+    __syncwarp();
+}
+
+template <int PM>
+__global__ void __launch_bounds__(Q2_THREADS, 1) k_query3(const FrameJob* __restrict__ jobs, const uint32_t* __restrict__ cent_prefix,
+                                                          int F, uint32_t smem_words_cap) {
+    extern __shared__ __align__(128) uint32_t dyn[];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t buf = smem_u32(dyn + warp * Q3_WARP_WORDS);
+    const uint32_t pacc = buf + 4u * Q3_BUF + 8u * Q2_RING;
+    uint32_t* sbits = dyn + Q2_WARPS * Q3_WARP_WORDS;
+    const uint32_t sb_addr = smem_u32(sbits);
+    sts128_if(pacc + 16u * lane, 0u, 0u, 0u, 0u, true);
+    const uint32_t total = cent_prefix[F];
+    const uint32_t lo = (uint32_t)(((uint64_t)total * blockIdx.x) / gridDim.x);
+    const uint32_t hi = (uint32_t)(((uint64_t)total * (blockIdx.x + 1)) / gridDim.x);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (lo >= hi) return;
+    int f = 0;
+    { int a = 0, b = F; while (a < b) { int m = (a + b) >> 1; if (cent_prefix[m + 1] > lo) b = m; else a = m + 1; } f = a; }
+    uint32_t parity = 0, g = lo;
+    while (g < hi) {
+        while (cent_prefix[f + 1] <= g) f++;
+        const FrameJob& J = jobs[f];
+        const uint32_t seg_end = min(hi, cent_prefix[f + 1]);
+        const uint32_t c_begin = g - cent_prefix[f], c_end = seg_end - cent_prefix[f];
+        const uint32_t nwords = (J.l + 31u) >> 5;
+        const uint32_t sw = min((nwords + 3u) & ~3u, smem_words_cap);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&bar, sw * 4u);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(J.bits);
+            uint8_t* dst = reinterpret_cast<uint8_t*>(sbits);
+            for (uint32_t off = 0; off < sw * 4u; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, sw * 4u - off), &bar);
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+        const FilterK K = filter_consts(J);
+        uint4* pass4 = reinterpret_cast<uint4*>(J.pass);
+        for (uint32_t slab = c_begin + 32u * warp; slab < c_end; slab += 32u * Q2_WARPS) {
+            const uint32_t last = min(slab + 31u, c_end - 1u);
+            const bool uniform = slab >= 1u && ndigits_u32(slab) == ndigits_u32(last) && K.fk >= 1u && K.fm.fast && K.fm.m <= (1u << 23);
+            if (uniform) {
+#define RBF_TILED(KD)                                                                                                                   \
+    if (K.fk == 3u) query_slab_tiled<KD, 3, PM>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, buf);                       \
+    else if (K.fk == 2u) query_slab_tiled<KD, 2, PM>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, buf);                  \
+    else query_slab_tiled<KD, 0, PM>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, buf);
+                switch (make_century(slab).kind) {
+                case K_4B: { RBF_TILED(K_4B) } break;
+                case K_8B: { RBF_TILED(K_8B) } break;
+                case K_44: { RBF_TILED(K_44) } break;
+                case K_88: { RBF_TILED(K_88) } break;
+                default:   { RBF_TILED(K_BB) } break;
+                }
+#undef RBF_TILED
+            } else {                                    // century 0, a digit-count boundary, floor_k == 0 or a huge filter
+                const uint32_t c = slab + lane;
+                if (c < c_end) {
+                    BitView bv; bv.sm = sbits; bv.gl = J.bits; bv.sm_words = sw;
+                    const Bits128 r = query_century(bv, K, c, min(100u, J.n - 100u * c));
+                    pass4[c] = make_uint4((uint32_t)r.lo, (uint32_t)(r.lo >> 32), (uint32_t)r.hi, (uint32_t)(r.hi >> 32));
+                }
+            }
+        }
+        g = seg_end;
+    }
 }
 
 template <int KIND, int PM, int ALG = 0>
@@ -1542,7 +1758,30 @@ cudaError_t launch_query(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, 
     int cap = smem_bytes_cap & ~15;
     if (cap > query_max_smem_bytes()) cap = query_max_smem_bytes() & ~15;
     const uint32_t need_words = (((max_l_bits + 31u) >> 5) + 3u) & ~3u;
+    if (variant == 4 && max_l_bits <= (1u << 23)) {       // decade tiles (records carry 23-bit indices)
+        const int qbytes = Q2_WARPS * Q3_WARP_WORDS * 4;
+        if (cap < qbytes + 1024) cap = qbytes + 1024;
+        const int bits_cap = cap - qbytes;
+        const bool fits = (size_t)need_words * 4 <= (size_t)bits_cap;
+        const int smem = qbytes + (fits ? (int)(need_words * 4 < 16 ? 16 : need_words * 4) : bits_cap);
+        uint32_t grid = (uint32_t)sm_count;
+        const uint32_t max_useful = (total_centuries + Q2_THREADS - 1) / Q2_THREADS;
+        if (grid > max_useful) grid = max_useful;
+        if (grid < 1u) grid = 1u;
+        cudaError_t e;
+        if (fits) {
+            e = cudaFuncSetAttribute(k_query3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            k_query3<0><<<grid, Q2_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F, (uint32_t)((smem - qbytes) / 4));
+        } else {
+            e = cudaFuncSetAttribute(k_query3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            k_query3<1><<<grid, Q2_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F, (uint32_t)((smem - qbytes) / 4));
+        }
+        return cudaGetLastError();
+    }
     if (variant >= 1) {                                   // staged, queue-compacted kernels
+        if (variant == 4) variant = 1;
         const int qbytes = Q2_WARPS * Q2_WARP_WORDS * 4;
         if (cap < qbytes + 1024) cap = qbytes + 1024;
         const int bits_cap = cap - qbytes;
