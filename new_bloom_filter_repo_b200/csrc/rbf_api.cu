@@ -31,7 +31,8 @@ struct rbf_ctx {
     int sm_count = 0;
     int k1_variant = 0;
     int insert_variant = 1; // 1: dense warp-compacted K2, 0: per-lane K2
-    int query_variant = 1;  // 0: per-lane; 1: staged A->B->C rings, L2 tail; 2: staged + 2-CTA DSMEM clusters; 3: dense A+B, ring before C
+    int query_variant = 4;  // 0: per-lane; 1: staged A->B->C rings, L2 tail; 2: staged + 2-CTA DSMEM clusters; 3: dense A+B, ring before C;
+                            // 4: decade tiles (m <= 2^23, else 1)
     int k1_only = 0;        // stop after K1 (mask + counts): VideoFrameCompressor._calculate_frame_diff
     int mask_mode = 0;      // 0: |dY| > thr (ivc:808); 1: additionally any byte of the pixel differs
     int query_smem_cap = 0;

@@ -134,6 +134,27 @@ def test_compress_vs_oracle_ragged_sizes(pkg, co, n, p_gen, seed):
     assert np.array_equal(dec, m)
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("n,p_gen,seed", [(101, 0.1, 21), (99999, 0.12, 22), (2073600, 0.0499, 23), (8294400, 0.03, 24),
+                                          (8294400, 0.19, 25), (33177600, 0.08, 26)])
+def test_query_kernel_variants_vs_oracle(pkg, co, variant, n, p_gen, seed):
+    """Every K3 formulation (per-lane, staged rings, DSMEM cluster, dense A+B, decade tiles) gives the oracle's
+    bitmap and witness bit for bit; the last size has l > 2^23, where the decade-tile kernel hands over to the rings."""
+    L, ctx = pkg._cabi.lib(), pkg._cabi.ctx()
+    m = mask_for({"n": n, "p_gen": p_gen, "seed": seed})
+    ob, ow, op, on, oratio, ok, ol = co.compress(m)
+    assert ok > 0
+    pkg._cabi.check(L.rbf_set_option(ctx, b"query_variant", variant), ctx)
+    try:
+        comp = pkg.BloomFilterCompressor()
+        bitmap, witness, p, nn, ratio = comp.compress(m)
+        assert len(bitmap) == ol and np.array_equal(bitmap, ob)
+        assert np.array_equal(np.array(witness, dtype=np.uint8), ow)
+        assert np.array_equal(comp.decompress(bitmap, witness, n, ok), m)
+    finally:
+        L.rbf_set_option(ctx, b"query_variant", 4)
+
+
 def test_decompress_short_witness_raises(pkg):
     m = mask_for({"n": 5000, "p_gen": 0.05, "seed": 3})
     comp = pkg.BloomFilterCompressor()
