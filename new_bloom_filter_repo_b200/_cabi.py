@@ -11,7 +11,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "librbf_b200.so")
+SO_PATH = os.environ.get("RBF_B200_LIB") or os.path.join(_HERE, "librbf_b200.so")
 
 _lib = None
 _ctx = None

@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(I2_WARPS * 32) k_insert2(const FrameJob* __res
     __shared__ uint64_t s_cs[I2_WARPS][32 * 3];
     __shared__ uint16_t s_list[I2_WARPS][I2_LIST];
     const FilterK K = filter_consts(J);
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31u;   // warp-uniform for the compiler
     const uint32_t ncent = (J.n + 99u) / 100u;
     const uint32_t nslab = (ncent + 31u) / 32u;
     for (uint32_t sl = blockIdx.x * I2_WARPS + warp; sl < nslab; sl += gridDim.x * I2_WARPS) {
@@ -716,7 +716,7 @@ __device__ __forceinline__ uint32_t probe_bit(uint32_t sm_addr, uint32_t sm_addr
 __device__ __forceinline__ uint32_t mod_fast(uint64_t h, const FastMod& f) {
     const uint32_t hh = (uint32_t)(h >> 32), hl = (uint32_t)h;
     const uint32_t q = hh * f.Mh + __umulhi(hh, f.Ml) + __umulhi(hl, f.Mh);
-    uint32_t r = hl - q * f.m;
+    uint32_t r = q * (0u - f.m) + hl;                                  // one IMAD: -m is loop-invariant
     r = min(r, r - 2u * f.m);
     return min(r, r - f.m);
 }
@@ -955,7 +955,15 @@ __device__ __noinline__ void query_slab_dense(const FilterK K, uint32_t sm_addr,
 // buffer belong to the current decade).  Survivors of B go through the small stage-C ring as before.
 // Requires m <= 2^23 (4K and 8K frames); larger filters use the ring kernel.
 // ------------------------------------------------------------------------------------------
-constexpr int Q3_BUF = 320;                                          // survivors of one decade of a slab, worst case
+#ifndef RBF_Q3_WARPS
+#define RBF_Q3_WARPS 28
+#endif
+constexpr int Q3_WARPS = RBF_Q3_WARPS, Q3_THREADS = 32 * Q3_WARPS;
+#ifndef RBF_Q3_TY
+#define RBF_Q3_TY 10
+#endif
+constexpr int Q3_TY = RBF_Q3_TY;                                        // positions of a decade per lane and tile: 10 or 5
+constexpr int Q3_BUF = 32 * Q3_TY;                                       // survivors of one tile of a slab, worst case
 constexpr int Q3_WARP_WORDS = Q3_BUF + (Q2_RING * 8 + 32 * 16 + 128) / 4;   // decade buffer, C ring, pass accumulators, digit table
 
 __device__ __forceinline__ void sts32_if(uint32_t addr, uint32_t v, bool p) {
@@ -986,8 +994,13 @@ __device__ __forceinline__ void drain_c_ring(const FilterK& K, uint32_t sm_addr,
     deliver_pass(pacc_addr, tag, have && (!(hA < K.T) || pb != 0u));
 }
 
+#ifdef RBF_Q3_INLINE
+#define RBF_Q3_FN __forceinline__
+#else
+#define RBF_Q3_FN __noinline__
+#endif
 template <int KIND, int FKT, int PM>
-__device__ __noinline__ void query_slab_tiled(const FilterK K, uint32_t sm_addr, uint32_t sm_addr1,
+__device__ RBF_Q3_FN void query_slab_tiled(const FilterK K, uint32_t sm_addr, uint32_t sm_addr1,
                                               const uint32_t* __restrict__ gl, uint32_t sm_words,
                                               const uint32_t* __restrict__ mask, uint32_t n, uint32_t slab_c0,
                                               uint32_t c_end, uint4* __restrict__ pass4, uint32_t buf_addr) {
@@ -1011,16 +1024,19 @@ __device__ __noinline__ void query_slab_tiled(const FilterK K, uint32_t sm_addr,
         const uint64_t D2 = decade_prep<KIND>(decade_state_t<KIND>(C2, K.s2, x));
         const uint32_t p0 = 10u * x;
         const uint64_t sh = (p0 < 64u) ? ((skip_lo >> p0) | (p0 ? (skip_hi << (64u - p0)) : 0ull)) : (skip_hi >> (p0 - 64u));
-        // ---- stage A: ten positions per lane, y compile-time
-        uint32_t idx0[10];
+#pragma unroll
+        for (int h = 0; h < 10 / Q3_TY; h++) {
+        // ---- stage A: Q3_TY positions per lane, y compile-time
+        uint32_t idx0[Q3_TY];
         uint32_t sv = 0;
 #pragma unroll
-        for (int y = 0; y < 10; y++) {
-            idx0[y] = mod_fast(finish_prep<KIND>(D1, K.s1, (uint32_t)y, rot_digit_const((uint32_t)y)), K.fm);
-            sv |= probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx0[y]) << y;
+        for (int yy = 0; yy < Q3_TY; yy++) {
+            const uint32_t y = (uint32_t)(h * Q3_TY + yy);
+            idx0[yy] = mod_fast(finish_prep<KIND>(D1, K.s1, y, rot_digit_const(y)), K.fm);
+            sv |= probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx0[yy]) << yy;
         }
-        sv &= ~(uint32_t)sh & 0x3ffu;
-        // ---- one scan per decade places the survivors
+        sv &= ~(uint32_t)(sh >> (h * Q3_TY)) & ((1u << Q3_TY) - 1u);
+        // ---- one scan per tile places the survivors
         const uint32_t cnt = __popc(sv);
         uint32_t inc = cnt;
 #pragma unroll
@@ -1032,9 +1048,9 @@ __device__ __noinline__ void query_slab_tiled(const FilterK K, uint32_t sm_addr,
         uint32_t off = buf_addr + 4u * (inc - cnt);
         const uint32_t ltag = lane << 23;
 #pragma unroll
-        for (int y = 0; y < 10; y++) {
-            const bool p = ((sv >> y) & 1u) != 0u;
-            sts32_if(off, idx0[y] | ltag | ((uint32_t)y << 28), p);
+        for (int yy = 0; yy < Q3_TY; yy++) {
+            const bool p = ((sv >> yy) & 1u) != 0u;
+            sts32_if(off, idx0[yy] | ltag | ((uint32_t)(h * Q3_TY + yy) << 28), p);
             off += p ? 4u : 0u;
         }
         __syncwarp();
@@ -1075,7 +1091,8 @@ __device__ __noinline__ void query_slab_tiled(const FilterK K, uint32_t sm_addr,
                 deliver_pass(pacc_addr, tag, ok != 0u);
             }
         }
-        __syncwarp();                                                // the decade buffer is rewritten next
+        __syncwarp();                                                // the tile buffer is rewritten next
+        }
     }
 #pragma unroll 1
     while (qc_cnt) drain_c_ring<KIND, PM>(K, sm_addr, sm_addr1, gl, sm_words, qc_addr, pacc_addr, lane, CA, qc_head, qc_cnt);
@@ -1093,14 +1110,14 @@ __device__ __noinline__ void query_slab_tiled(const FilterK K, uint32_t sm_addr,
 }
 
 template <int PM>
-__global__ void __launch_bounds__(Q2_THREADS, 1) k_query3(const FrameJob* __restrict__ jobs, const uint32_t* __restrict__ cent_prefix,
+__global__ void __launch_bounds__(Q3_THREADS, 1) k_query3(const FrameJob* __restrict__ jobs, const uint32_t* __restrict__ cent_prefix,
                                                           int F, uint32_t smem_words_cap) {
     extern __shared__ __align__(128) uint32_t dyn[];
     __shared__ __align__(8) uint64_t bar;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31u;   // warp-uniform for the compiler
     const uint32_t buf = smem_u32(dyn + warp * Q3_WARP_WORDS);
     const uint32_t pacc = buf + 4u * Q3_BUF + 8u * Q2_RING;
-    uint32_t* sbits = dyn + Q2_WARPS * Q3_WARP_WORDS;
+    uint32_t* sbits = dyn + Q3_WARPS * Q3_WARP_WORDS;
     const uint32_t sb_addr = smem_u32(sbits);
     sts128_if(pacc + 16u * lane, 0u, 0u, 0u, 0u, true);
     const uint32_t total = cent_prefix[F];
@@ -1131,7 +1148,7 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_query3(const FrameJob* __rest
         parity ^= 1u;
         const FilterK K = filter_consts(J);
         uint4* pass4 = reinterpret_cast<uint4*>(J.pass);
-        for (uint32_t slab = c_begin + 32u * warp; slab < c_end; slab += 32u * Q2_WARPS) {
+        for (uint32_t slab = c_begin + 32u * warp; slab < c_end; slab += 32u * Q3_WARPS) {
             const uint32_t last = min(slab + 31u, c_end - 1u);
             const bool uniform = slab >= 1u && ndigits_u32(slab) == ndigits_u32(last) && K.fk >= 1u && K.fm.fast && K.fm.m <= (1u << 23);
             if (uniform) {
@@ -1182,7 +1199,7 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_query2(const FrameJob* __rest
                                                           uint32_t smem_words_cap) {
     extern __shared__ __align__(128) uint32_t dyn[];
     __shared__ __align__(8) uint64_t bar;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31u;   // warp-uniform for the compiler
     uint32_t* wq = dyn + warp * Q2_WARP_WORDS;
     const uint32_t qb = smem_u32(wq), qc = smem_u32(wq + Q2_RING * 4), pacc = smem_u32(wq + Q2_RING * 4 + Q2_RING * 2);
     uint32_t* sbits = dyn + Q2_WARPS * Q2_WARP_WORDS;
@@ -1259,7 +1276,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q2_THREADS, 1)
 k_query2c(const FrameJob* __restrict__ jobs, const uint32_t* __restrict__ cent_prefix, int F, uint32_t half_words_cap) {
     extern __shared__ __align__(128) uint32_t dyn[];
     __shared__ __align__(8) uint64_t bar;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31u;   // warp-uniform for the compiler
     const uint32_t rank = cluster_ctarank();
     const uint32_t cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
     uint32_t* wq = dyn + warp * Q2_WARP_WORDS;
@@ -1759,24 +1776,24 @@ cudaError_t launch_query(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, 
     if (cap > query_max_smem_bytes()) cap = query_max_smem_bytes() & ~15;
     const uint32_t need_words = (((max_l_bits + 31u) >> 5) + 3u) & ~3u;
     if (variant == 4 && max_l_bits <= (1u << 23)) {       // decade tiles (records carry 23-bit indices)
-        const int qbytes = Q2_WARPS * Q3_WARP_WORDS * 4;
+        const int qbytes = Q3_WARPS * Q3_WARP_WORDS * 4;
         if (cap < qbytes + 1024) cap = qbytes + 1024;
         const int bits_cap = cap - qbytes;
         const bool fits = (size_t)need_words * 4 <= (size_t)bits_cap;
         const int smem = qbytes + (fits ? (int)(need_words * 4 < 16 ? 16 : need_words * 4) : bits_cap);
         uint32_t grid = (uint32_t)sm_count;
-        const uint32_t max_useful = (total_centuries + Q2_THREADS - 1) / Q2_THREADS;
+        const uint32_t max_useful = (total_centuries + Q3_THREADS - 1) / Q3_THREADS;
         if (grid > max_useful) grid = max_useful;
         if (grid < 1u) grid = 1u;
         cudaError_t e;
         if (fits) {
             e = cudaFuncSetAttribute(k_query3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return e;
-            k_query3<0><<<grid, Q2_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F, (uint32_t)((smem - qbytes) / 4));
+            k_query3<0><<<grid, Q3_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F, (uint32_t)((smem - qbytes) / 4));
         } else {
             e = cudaFuncSetAttribute(k_query3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return e;
-            k_query3<1><<<grid, Q2_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F, (uint32_t)((smem - qbytes) / 4));
+            k_query3<1><<<grid, Q3_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F, (uint32_t)((smem - qbytes) / 4));
         }
         return cudaGetLastError();
     }
