@@ -169,6 +169,7 @@ static void job_set_filter(FrameJob& J, uint64_t size, double k_star, const rbf_
     J.act_T = rbf_activation_threshold(p_act);
     J.seed1 = sd.h1; J.seed2 = sd.h2; J.seedA = sd.act;
     J.fm = make_fastmod((uint32_t)size);
+    J.neg_m = 0u - (uint32_t)size;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -383,11 +383,11 @@ __global__ void __launch_bounds__(256) k_threshold_tail(const PairJob* __restric
 struct FilterK {
     FastMod fm;
     uint64_t T, s1, s2, sA;
-    uint32_t fk, has_act;
+    uint32_t fk, has_act, nm;
 };
 __device__ __forceinline__ FilterK filter_consts(const FrameJob& J) {
     FilterK k;
-    k.fm = J.fm; k.T = J.act_T; k.s1 = J.seed1; k.s2 = J.seed2; k.sA = J.seedA; k.fk = J.floor_k; k.has_act = J.has_act;
+    k.fm = J.fm; k.T = J.act_T; k.s1 = J.seed1; k.s2 = J.seed2; k.sA = J.seedA; k.fk = J.floor_k; k.has_act = J.has_act; k.nm = J.neg_m;
     return k;
 }
 
@@ -713,10 +713,10 @@ __device__ __forceinline__ uint32_t probe_bit(uint32_t sm_addr, uint32_t sm_addr
 }
 
 // fast reductions for 2 <= m <= 2^30 (the staged kernel is only launched then)
-__device__ __forceinline__ uint32_t mod_fast(uint64_t h, const FastMod& f) {
+__device__ __forceinline__ uint32_t mod_fast(uint64_t h, const FastMod& f, uint32_t neg_m) {
     const uint32_t hh = (uint32_t)(h >> 32), hl = (uint32_t)h;
     const uint32_t q = hh * f.Mh + __umulhi(hh, f.Ml) + __umulhi(hl, f.Mh);
-    uint32_t r = q * (0u - f.m) + hl;                                  // one IMAD: -m is loop-invariant
+    uint32_t r = q * neg_m + hl;                                       // hl - q*m in one IMAD (neg_m = 2^32 - m from the host)
     r = min(r, r - 2u * f.m);
     return min(r, r - f.m);
 }
@@ -748,7 +748,7 @@ __device__ __forceinline__ void drain_stages(const FilterK& K, uint32_t sm_addr,
         R.qb_head = (R.qb_head + nb) & (Q2_RING - 1);
         R.qb_cnt -= nb;
         const uint64_t rbB = kind_ends_in_byte<KIND>() ? ({ const uint2 t = lds64(pacc_addr + 512u + 8u * (r.y & 15u)); (uint64_t)t.x | ((uint64_t)t.y << 32); }) : 0ull;
-        const uint32_t stepm = have ? mod_fast(finish_prep<KIND>((uint64_t)r.z | ((uint64_t)r.w << 32), K.s2, r.y & 15u, rbB), K.fm) : 0u;
+        const uint32_t stepm = have ? mod_fast(finish_prep<KIND>((uint64_t)r.z | ((uint64_t)r.w << 32), K.s2, r.y & 15u, rbB), K.fm, K.nm) : 0u;
         uint32_t idx = have ? r.x : 0u;
         uint32_t ok = have ? 1u : 0u;
         if (FKT > 0) {                                               // floor_k known at compile time: straight-line probes
@@ -819,8 +819,8 @@ __device__ __noinline__ void query_slab_staged(const FilterK K, uint32_t sm_addr
         const uint32_t tagx = (lane << 8) | (x << 4);
 #pragma unroll 1
         for (uint32_t y = 0; y < 10u; y += 2u) {                     // ---- stage A: two positions per lane (ILP)
-            const uint32_t idxA = mod_fast(finish_prep<KIND>(D1, K.s1, y, c_rot_digit[y]), K.fm);
-            const uint32_t idxB = mod_fast(finish_prep<KIND>(D1, K.s1, y + 1u, c_rot_digit[y + 1u]), K.fm);
+            const uint32_t idxA = mod_fast(finish_prep<KIND>(D1, K.s1, y, c_rot_digit[y]), K.fm, K.nm);
+            const uint32_t idxB = mod_fast(finish_prep<KIND>(D1, K.s1, y + 1u, c_rot_digit[y + 1u]), K.fm, K.nm);
             const uint32_t bA = probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idxA);
             const uint32_t bB = probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idxB);
             const bool svA = (bA & ~(skip10 >> y) & 1u) != 0u;
@@ -893,8 +893,8 @@ __device__ __noinline__ void query_slab_dense(const FilterK K, uint32_t sm_addr,
 #pragma unroll 1
         for (uint32_t y = 0; y < 10u; y++) {
             if (feeding) {                                           // ---- stages A + B, every position
-                const uint32_t idx0 = mod_fast(finish_t<KIND>(D1, K.s1, y), K.fm);
-                const uint32_t stepm = mod_fast(finish_t<KIND>(D2, K.s2, y), K.fm);
+                const uint32_t idx0 = mod_fast(finish_t<KIND>(D1, K.s1, y), K.fm, K.nm);
+                const uint32_t stepm = mod_fast(finish_t<KIND>(D2, K.s2, y), K.fm, K.nm);
                 uint32_t ok = probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx0) & ~(skip10 >> y) & 1u;
                 uint32_t idx = idx0;
                 if (FKT > 0) {
@@ -1032,7 +1032,7 @@ __device__ RBF_Q3_FN void query_slab_tiled(const FilterK K, uint32_t sm_addr, ui
 #pragma unroll
         for (int yy = 0; yy < Q3_TY; yy++) {
             const uint32_t y = (uint32_t)(h * Q3_TY + yy);
-            idx0[yy] = mod_fast(finish_prep<KIND>(D1, K.s1, y, rot_digit_const(y)), K.fm);
+            idx0[yy] = mod_fast(finish_prep<KIND>(D1, K.s1, y, rot_digit_const(y)), K.fm, K.nm);
             sv |= probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx0[yy]) << yy;
         }
         sv &= ~(uint32_t)(sh >> (h * Q3_TY)) & ((1u << Q3_TY) - 1u);
@@ -1065,7 +1065,7 @@ __device__ RBF_Q3_FN void query_slab_tiled(const FilterK K, uint32_t sm_addr, ui
                                  ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(D2 >> 32), owner) << 32);
             uint64_t rb = 0;
             if (kind_ends_in_byte<KIND>()) { const uint2 t = lds64(rb_addr + 8u * y); rb = (uint64_t)t.x | ((uint64_t)t.y << 32); }
-            const uint32_t stepm = have ? mod_fast(finish_prep<KIND>(D2o, K.s2, y, rb), K.fm) : 0u;
+            const uint32_t stepm = have ? mod_fast(finish_prep<KIND>(D2o, K.s2, y, rb), K.fm, K.nm) : 0u;
             uint32_t idx = have ? (rec & 0x7fffffu) : 0u;
             uint32_t ok = have ? 1u : 0u;
             if (FKT > 0) {

@@ -26,7 +26,7 @@ struct FrameJob {
     uint32_t* witness;    // witness bit stream (K3b output / K4b input), zeroed before K3b
     uint32_t* out_mask;   // decode output, natural packing, zeroed before K4b
     uint32_t wlen_in;     // decode: number of valid witness bits
-    uint32_t pad0;
+    uint32_t neg_m;       // 2^32 - l, for the one-instruction remainder step of the query kernels
 };
 
 // One frame pair for the threshold kernel (ivc:788-808).
