@@ -1420,21 +1420,23 @@ __global__ void __launch_bounds__(1024) k_witness(const FrameJob* __restrict__ j
             const Bits128 mb = load_bits100(J.mask, c, min(100u, J.n - 100u * c));
             const uint32_t P[4] = {p.x, p.y, p.z, p.w};
             const uint32_t M[4] = {(uint32_t)mb.lo, (uint32_t)(mb.lo >> 32), (uint32_t)mb.hi, (uint32_t)(mb.hi >> 32)};
+            // witness bit k = mask bit of the k-th passing position: walk the (few) members, not the passes --
+            // a member's k is its rank among the passing positions
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                uint32_t pw = P[j];
-                while (pw) {
-                    const uint32_t b = __ffs(pw) - 1;
-                    pw &= pw - 1u;
-                    const uint64_t bit = (M[j] >> b) & 1u;
-                    if (cnt < 64u) wlo |= bit << cnt; else whi |= bit << (cnt - 64u);
-                    cnt++;
+                uint32_t mw = M[j] & P[j];
+                while (mw) {
+                    const uint32_t b = __ffs(mw) - 1;
+                    mw &= mw - 1u;
+                    const uint32_t k = cnt + __popc(P[j] & ((1u << b) - 1u));
+                    if (k < 64u) wlo |= 1ull << k; else whi |= 1ull << (k - 64u);
                 }
+                cnt += __popc(P[j]);
             }
         }
         uint32_t tot;
         const uint32_t off = block_excl_scan(cnt, s_warp, tot);
-        if (cnt) or_bits128(J.witness, (uint64_t)base + off, wlo, whi);
+        if (wlo | whi) or_bits128(J.witness, (uint64_t)base + off, wlo, whi);
         base += tot;
     }
     if (threadIdx.x == 0 && blockIdx.x == chunks - 1) wlen_out[blockIdx.y] = base;
@@ -1854,7 +1856,7 @@ cudaError_t launch_witness(const FrameJob* d_jobs, int F, uint32_t max_centuries
     const uint32_t ch = witness_chunks(F, max_centuries, sm_count);
     if (ch > 1u) k_pass_count<<<dim3(ch, (unsigned)F), 256, 0, st>>>(d_jobs, ch, d_scratch);
     k_witness<<<dim3(ch, (unsigned)F), 1024, 0, st>>>(d_jobs, ch, d_scratch, d_wlen);
-    k_finalize<<<dim3(8, (unsigned)F), 256, 0, st>>>(d_jobs, d_wlen);
+    k_finalize<<<dim3(32, (unsigned)F), 256, 0, st>>>(d_jobs, d_wlen);
     return cudaGetLastError();
 }
 cudaError_t launch_expand(const FrameJob* d_jobs, int F, uint32_t max_centuries, int sm_count, uint32_t* d_scratch, uint32_t* d_consumed,
