@@ -295,8 +295,9 @@ def run_ours(args):
         q_ms = stage["k3_query"]
         coded_px = sum(r.n for r in res if not r.raw)
         traffic = None
-        try:                                     # dram bytes per launch of k_query2 from the committed ncu --set full capture
-            with open(os.path.join(ROOT, "profiles", "r01_k_query2_traffic.json")) as f:
+        qkernel = "k_query3" if args.query_variant == 4 else "k_query2"
+        try:                                     # dram bytes per launch of the query kernel from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r01_%s_traffic.json" % qkernel)) as f:
                 traffic = json.load(f)["dram_bytes_per_pair"] * sum(1 for r in res if not r.raw)
         except Exception:
             pass
@@ -313,7 +314,7 @@ def run_ours(args):
                        "k1_variant": "tma-bulk-ring" if args.k1_variant == 1 else "ldg256",
                        "query_variant": {0: "per-lane", 1: "staged-rings", 2: "staged-rings+dsmem-cluster", 3: "dense-A+B", 4: "decade-tiles"}.get(args.query_variant),
                        "mean_l_bits": float(np.mean([r.l for r in res])), "mean_witness_bits": float(np.mean([r.wlen for r in res]))},
-            "roofline": {"bound": "hbm", "kernel": "k_query2", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": qkernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": coded_px * BYTES_PER_PIXEL, "launch_ms": q_ms,
                          "pipeline_frac": value * 1e6 * BYTES_PER_PIXEL / 1e9 / world / peak,
