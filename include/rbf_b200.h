@@ -183,7 +183,9 @@ int rbf_stream_median5(rbf_stream* s, uint32_t frame, void* plane_out);   /* cha
 int rbf_nccl_unique_id(uint8_t id_out[128]);
 int rbf_nccl_init(rbf_ctx* ctx, const uint8_t id[128], int rank, int nranks);
 int rbf_nccl_allgather(rbf_ctx* ctx, const void* d_send, void* d_recv, uint64_t bytes_per_rank);
-/* compact `pairs` bitmap slots (slot_bytes each) into d_send and all-gather them into d_recv */
+/* compact `pairs` bitmap slots (slot_bytes each) into d_send and all-gather them into d_recv.  Enqueued on the context's
+ * communication stream so that the next rbf_stream_encode overlaps the exchange; d_recv is complete after rbf_sync,
+ * rbf_timer_stop_ms or rbf_memcpy_d2h. */
 int rbf_stream_allgather_bitmaps(rbf_stream* s, uint32_t pairs, uint64_t slot_bytes, void* d_send, void* d_recv);
 int rbf_nccl_destroy(rbf_ctx* ctx);
 

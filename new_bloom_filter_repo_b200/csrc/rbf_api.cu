@@ -25,6 +25,9 @@ struct rbf_ctx {
     int device = -1;
     cudaStream_t st = nullptr;
     cudaStream_t st_copy = nullptr;   // H2D of frame chunks in rbf_stream_encode_host
+    cudaStream_t st_comm = nullptr;   // slot packing + ncclAllGather of rbf_stream_allgather_bitmaps (overlaps the next encode)
+    cudaEvent_t ev_enc = nullptr, ev_pack = nullptr, ev_comm = nullptr;
+    bool pack_pending = false, comm_pending = false;
     int host_chunk_frames = 32;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaDeviceProp prop;
@@ -216,6 +219,10 @@ extern "C" void rbf_ctx_destroy(rbf_ctx* c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->st) cudaStreamDestroy(c->st);
     if (c->st_copy) cudaStreamDestroy(c->st_copy);
+    if (c->st_comm) { cudaStreamSynchronize(c->st_comm); cudaStreamDestroy(c->st_comm); }
+    if (c->ev_enc) cudaEventDestroy(c->ev_enc);
+    if (c->ev_pack) cudaEventDestroy(c->ev_pack);
+    if (c->ev_comm) cudaEventDestroy(c->ev_comm);
     delete c;
 }
 extern "C" const char* rbf_last_error(const rbf_ctx* c) { return c ? c->err : g_err; }
@@ -252,10 +259,26 @@ extern "C" int64_t rbf_get_counter(rbf_ctx* c, const char* key) {
     return -1;
 }
 extern "C" int rbf_reset_counters(rbf_ctx* c) { if (!c) return RBF_ERR_INVALID; c->launches = c->h2d = c->d2h = 0; return RBF_OK; }
-extern "C" int rbf_sync(rbf_ctx* c) { if (!c) return RBF_ERR_INVALID; CK(c, cudaStreamSynchronize(c->st)); return RBF_OK; }
+// before the bit arrays are overwritten: the slot packing of a pending all-gather must have read them
+static int wait_pack(rbf_ctx* c) {
+    if (c->pack_pending) { CK(c, cudaStreamWaitEvent(c->st, c->ev_pack, 0)); c->pack_pending = false; }
+    return RBF_OK;
+}
+// make the context's stream wait for an all-gather still running on the communication stream
+static int join_comm(rbf_ctx* c) {
+    if (c->comm_pending) { CK(c, cudaStreamWaitEvent(c->st, c->ev_comm, 0)); c->comm_pending = false; c->pack_pending = false; }
+    return RBF_OK;
+}
+extern "C" int rbf_sync(rbf_ctx* c) {
+    if (!c) return RBF_ERR_INVALID;
+    if (int r = join_comm(c)) return r;
+    CK(c, cudaStreamSynchronize(c->st));
+    return RBF_OK;
+}
 extern "C" int rbf_timer_start(rbf_ctx* c) { if (!c) return RBF_ERR_INVALID; CK(c, cudaEventRecord(c->ev0, c->st)); return RBF_OK; }
 extern "C" int rbf_timer_stop_ms(rbf_ctx* c, double* ms) {
     if (!c || !ms) return RBF_ERR_INVALID;
+    if (int r = join_comm(c)) return r;
     CK(c, cudaEventRecord(c->ev1, c->st));
     CK(c, cudaEventSynchronize(c->ev1));
     float f = 0;
@@ -275,6 +298,7 @@ extern "C" int rbf_memcpy_h2d(rbf_ctx* c, void* d, const void* h, size_t n) {
 }
 extern "C" int rbf_memcpy_d2h(rbf_ctx* c, void* h, const void* d, size_t n) {
     if (!c) return RBF_ERR_INVALID;
+    if (int r = join_comm(c)) return r;
     CK(c, cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c->st)); CK(c, cudaStreamSynchronize(c->st)); c->d2h += n; return RBF_OK;
 }
 extern "C" int rbf_memset(rbf_ctx* c, void* d, int v, size_t n) { if (!c) return RBF_ERR_INVALID; CK(c, cudaMemsetAsync(d, v, n, c->st)); return RBF_OK; }
@@ -681,6 +705,7 @@ static int stream_encode_range(rbf_stream* s, uint32_t first, uint32_t count, ui
     if (coded_pairs == 0 || c->k1_only) return RBF_OK;
     CK(c, cudaMemcpyAsync(s->d_jobs + first, s->h_jobs + first, sizeof(FrameJob) * count, cudaMemcpyHostToDevice, c->st));
     CK(c, cudaMemcpyAsync(s->d_prefix + pfx, hp, 4 * ((size_t)count + 1), cudaMemcpyHostToDevice, c->st));
+    if (int r = wait_pack(c)) return r;                  // the slots of the last all-gather are packed
     CK(c, cudaMemsetAsync(s->d_bits + (size_t)first * s->mask_stride_w, 0, s->mask_stride_w * 4 * count, c->st));
     CK(c, cudaMemsetAsync(s->d_wit + (size_t)first * s->mask_stride_w, 0, s->mask_stride_w * 4 * count, c->st));
     if (record_events) CK(c, cudaEventRecord(s->ev[2], c->st));
@@ -817,6 +842,7 @@ extern "C" int rbf_stream_decode_verify(rbf_stream* s, uint32_t pairs, uint64_t*
     if (!s->d_dec) CK(c, cudaMalloc((void**)&s->d_dec, stride_w * 4 * s->max_pairs));
     CK(c, cudaMemsetAsync(s->d_dec, 0, stride_w * 4 * pairs, c->st));
     // bitmap and witness sit in packbits order after K3b; the kernels work LSB-first
+    if (int r = wait_pack(c)) return r;
     LAUNCH(c, launch_bitrev(s->d_bits, stride_w * pairs, c->st));
     LAUNCH(c, launch_bitrev(s->d_wit, stride_w * pairs, c->st));
     for (uint32_t i = 0; i < pairs; i++) {
@@ -1005,11 +1031,11 @@ extern "C" int rbf_nccl_init(rbf_ctx* c, const uint8_t id[128], int rank, int nr
     c->nccl_lib = h; c->nccl_comm = comm; c->rank = rank; c->nranks = nranks;
     return RBF_OK;
 }
-extern "C" int rbf_nccl_allgather(rbf_ctx* c, const void* d_send, void* d_recv, uint64_t bytes_per_rank) {
+static int nccl_allgather_on(rbf_ctx* c, const void* d_send, void* d_recv, uint64_t bytes_per_rank, cudaStream_t st) {
     if (!c || !c->nccl_comm) return set_err(c, RBF_ERR_STATE, "rbf_nccl_allgather: communicator not initialised");
     fn_AllGather f = (fn_AllGather)dlsym(c->nccl_lib, "ncclAllGather");
     if (!f) return set_err(c, RBF_ERR_NCCL, "ncclAllGather not found");
-    int r = f(d_send, d_recv, (size_t)bytes_per_rank, /*ncclUint8*/ 1, c->nccl_comm, c->st);
+    int r = f(d_send, d_recv, (size_t)bytes_per_rank, /*ncclUint8*/ 1, c->nccl_comm, st);
     if (r) {
         fn_GetErrorString es = (fn_GetErrorString)dlsym(c->nccl_lib, "ncclGetErrorString");
         return set_err(c, RBF_ERR_NCCL, "ncclAllGather failed: %s", es ? es(r) : "?");
@@ -1017,16 +1043,38 @@ extern "C" int rbf_nccl_allgather(rbf_ctx* c, const void* d_send, void* d_recv, 
     c->launches++;
     return RBF_OK;
 }
+extern "C" int rbf_nccl_allgather(rbf_ctx* c, const void* d_send, void* d_recv, uint64_t bytes_per_rank) {
+    return nccl_allgather_on(c, d_send, d_recv, bytes_per_rank, c ? c->st : nullptr);
+}
+// Packs the bit arrays of the last encode into fixed-size slots and all-gathers them on the context's communication
+// stream: the call returns once the work is enqueued, the next rbf_stream_encode overlaps it (it only waits for the
+// packing before it clears the bit arrays).  d_recv is complete after rbf_sync, rbf_timer_stop_ms or rbf_memcpy_d2h.
 extern "C" int rbf_stream_allgather_bitmaps(rbf_stream* s, uint32_t pairs, uint64_t slot_bytes, void* d_send, void* d_recv) {
     if (!s || !d_send || !d_recv) return set_err(s ? s->c : nullptr, RBF_ERR_INVALID, "rbf_stream_allgather_bitmaps: NULL");
     rbf_ctx* c = s->c;
     const size_t stride = s->mask_stride_w * 4;
     if (slot_bytes == 0 || slot_bytes > stride || pairs > s->max_pairs) return set_err(c, RBF_ERR_INVALID, "bad slot/pairs");
-    CK(c, cudaMemcpy2DAsync(d_send, slot_bytes, s->d_bits, stride, slot_bytes, pairs, cudaMemcpyDeviceToDevice, c->st));
-    return rbf_nccl_allgather(c, d_send, d_recv, slot_bytes * pairs);
+    if (!c->nccl_comm) return set_err(c, RBF_ERR_STATE, "rbf_stream_allgather_bitmaps: communicator not initialised");
+    if (!c->st_comm) {
+        CK(c, cudaStreamCreateWithFlags(&c->st_comm, cudaStreamNonBlocking));
+        CK(c, cudaEventCreateWithFlags(&c->ev_enc, cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+    }
+    CK(c, cudaEventRecord(c->ev_enc, c->st));                       // the encode that produced the bit arrays
+    CK(c, cudaStreamWaitEvent(c->st_comm, c->ev_enc, 0));
+    CK(c, cudaMemcpy2DAsync(d_send, slot_bytes, s->d_bits, stride, slot_bytes, pairs, cudaMemcpyDeviceToDevice, c->st_comm));
+    CK(c, cudaEventRecord(c->ev_pack, c->st_comm));
+    c->pack_pending = true;
+    if (int r = nccl_allgather_on(c, d_send, d_recv, slot_bytes * pairs, c->st_comm)) return r;
+    CK(c, cudaEventRecord(c->ev_comm, c->st_comm));
+    c->comm_pending = true;
+    return RBF_OK;
 }
 extern "C" int rbf_nccl_destroy(rbf_ctx* c) {
     if (!c) return RBF_ERR_INVALID;
+    if (c->st_comm) cudaStreamSynchronize(c->st_comm);
+    c->comm_pending = c->pack_pending = false;
     if (c->nccl_comm && c->nccl_lib) {
         fn_CommDestroy f = (fn_CommDestroy)dlsym(c->nccl_lib, "ncclCommDestroy");
         if (f) f(c->nccl_comm);

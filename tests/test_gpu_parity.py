@@ -390,12 +390,16 @@ def test_nccl_allgather_single_rank(pkg):
     cabi.check(cabi.lib().rbf_nccl_unique_id(cabi.ptr(ident)))
     cabi.check(cabi.lib().rbf_nccl_init(cabi.ctx(), cabi.ptr(ident), 0, 1), cabi.ctx())
     slot = (max((r.l + 7) // 8 for r in res) + 15) // 16 * 16
+    want = [st.fetch(t, want_mask=False)[0] for t in range(4)]
     send, recv = rdist.allgather_bitmaps(st, 4, slot, 1)
+    # the exchange runs on the communication stream: an encode issued right behind it (other bit arrays) must not disturb it
+    st.upload(synth_stream(270, 480, 5, 43, [0.1, 0.05]))
+    res2 = st.encode_consecutive(5, 3.0)
+    assert [r.ones for r in res2] != [r.ones for r in res]
     cabi.check(cabi.lib().rbf_sync(cabi.ctx()), cabi.ctx())
     got = recv.to_host().reshape(4, slot)
-    for t, r in enumerate(res):
-        bm, _, _ = st.fetch(t, want_mask=False)
-        assert np.array_equal(got[t, : len(bm)], bm)
+    for t in range(4):
+        assert np.array_equal(got[t, : len(want[t])], want[t])
     send.free(); recv.free()
     cabi.check(cabi.lib().rbf_nccl_destroy(cabi.ctx()), cabi.ctx())
     st.close()
