@@ -107,3 +107,68 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f
+
+
+# ------------------------------------------------------------------ randomized differentials of the exact host scalars
+def test_probe_index_random_vs_bigint(cabi):
+    """(h1 + i*h2) % m in unbounded integers (ivc:79-81) for random 64-bit hashes and awkward moduli."""
+    L = cabi.lib()
+    rng = np.random.default_rng(11)
+    ms = [1, 2, 3, 997, 2 ** 16, 2 ** 23, 2 ** 23 + 1, 1908859, 2 ** 30 - 1, 2 ** 30, 2 ** 30 + 1, 2 ** 31, 2 ** 32 - 1]
+    ms += [int(x) for x in rng.integers(1, 2 ** 32, 300)]
+    for m in ms:
+        for _ in range(20):
+            h1, h2 = (int(x) for x in rng.integers(0, 2 ** 64, 2, dtype=np.uint64))
+            if rng.random() < 0.1:
+                h1, h2 = 2 ** 64 - 1, 2 ** 64 - 1 - int(rng.integers(0, 3))
+            for i in (0, 1, 2, 7, 63):
+                assert L.rbf_probe_index(h1, h2, i, m) == (h1 + i * h2) % m, (h1, h2, i, m)
+
+
+def test_activation_threshold_is_the_exact_cut(cabi):
+    """h < T  <=>  h / (2**64 - 1) < p with Python's correctly rounded int/int division (ivc:95-97)."""
+    rng = np.random.default_rng(12)
+    D = 2 ** 64 - 1
+    ps = [0.5, 0.25, 0.1, 0.2999999999999998, 1e-9, 1 - 2 ** -53, 2 ** -64, 2 ** -60, 0.9999999999]
+    ps += [float(x) for x in rng.random(400)] + [float(x) for x in rng.random(100) * 1e-6]
+    for p in ps:
+        T = cabi.activation_threshold(p)
+        assert 0 <= T <= 2 ** 64
+        if T > 0:
+            assert (T - 1) / D < p, (p, T)
+        if T < 2 ** 64:
+            assert not (T / D < p), (p, T)
+    assert cabi.activation_threshold(0.0) == 0
+
+
+def test_optimal_params_random_vs_reference_expression(cabi):
+    """_calculate_optimal_params (ivc:161-196) restated with Python floats, against the library's host routine."""
+    import math
+    P_STAR = 0.32453
+
+    def ref(n, ones):
+        p = ones / n
+        if p >= P_STAR:
+            return False, p, 0.0, 0
+        if p <= 0.0001 or p >= P_STAR:
+            return False, p, 0.0, 0
+        L = math.log(2.0)
+        k = math.log2((1.0 - p) * math.pow(L, 2.0) / p)
+        if k <= 0 or math.isnan(k):
+            return False, p, 0.0, 0
+        l = int(p * n * k * (1.0 / L))
+        k, l = max(0.1, k), max(1, l)
+        return not (l == 0 or l >= n), p, k, l
+
+    rng = np.random.default_rng(13)
+    cases = [(n, int(n * f)) for n in (4096, 2073600, 8294400, 33177600) for f in (0.0, 0.00009, 0.0001, 0.00011, 0.05, 0.3245, 0.32453, 0.3246, 0.5, 1.0)]
+    for _ in range(3000):
+        n = int(rng.integers(1, 40_000_000))
+        cases.append((n, int(rng.integers(0, n + 1) * (rng.random() ** 3))))
+    for n, ones in cases:
+        coded, p, k, l = cabi.optimal_params(n, ones)
+        rc, rp, rk, rl = ref(n, ones)
+        assert float(p).hex() == float(rp).hex(), (n, ones)
+        assert bool(coded) == rc, (n, ones, k, l, rk, rl)
+        if rc:
+            assert (float(k).hex(), l) == (float(rk).hex(), rl), (n, ones)
