@@ -193,14 +193,35 @@ def pinned_array(cabi, shape, dtype=np.uint8):
     return np.frombuffer(buf, dtype=dtype).reshape(shape), p
 
 
+def bind_near_gpu(gpu_index: int) -> bool:
+    """N > 1: keep this rank (and the pinned frames it first-touches) on the CPUs NVML reports as local to its GPU, so
+    eight ranks streaming 55 GB/s each over PCIe do not all pull from one socket's memory.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) < 4:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    numa_bound = False
     if world > 1:
         import torch.distributed as dist                 # rendezvous / barriers only; the data path is the library's NCCL
         dist.init_process_group(backend="gloo")
+        numa_bound = bind_near_gpu(local)
     import new_bloom_filter_repo_b200 as pkg
     from new_bloom_filter_repo_b200 import _cabi as cabi, distributed as rdist
     L, ctx = cabi.lib(), cabi.ctx()
@@ -311,7 +332,7 @@ def run_ours(args):
                                    (F, pairs, "; frames sharded per rank + one NCCL all-gather of the bit arrays" if world > 1 else ""),
                        "height": H, "width": W, "frames": F, "pairs_per_gpu": pairs, "parallelism": "frame-sharded x%d" % world,
                        "l2_policy": "inputs larger than L2: %.2f GB of frames per step, no flush needed" % (F * n * 3 / 1e9),
-                       "k1_variant": "tma-bulk-ring" if args.k1_variant == 1 else "ldg256",
+                       "k1_variant": "tma-bulk-ring" if args.k1_variant == 1 else "ldg256", "rank_bound_to_gpu_numa_node": numa_bound,
                        "query_variant": {0: "per-lane", 1: "staged-rings", 2: "staged-rings+dsmem-cluster", 3: "dense-A+B", 4: "decade-tiles"}.get(args.query_variant),
                        "mean_l_bits": float(np.mean([r.l for r in res])), "mean_witness_bits": float(np.mean([r.wlen for r in res]))},
             "roofline": {"bound": "hbm", "kernel": qkernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
