@@ -264,18 +264,23 @@ def run_ours(args):
         cabi.check(L.rbf_sync(ctx), ctx)
 
     # multi-GPU: one all-gather of the packed bit arrays per step
-    send = recv = None
+    send = recv = peer = None
     slot = 0
     res = st.encode_consecutive(F, 3.0)
     if world > 1:
-        rdist.init_nccl_from_torch(dist)
         slot = rdist.agree_slot_bytes(dist, max(r.l for r in res))
-        send = rdist.DeviceBuffer(slot * pairs)
-        recv = rdist.DeviceBuffer(slot * pairs * world)
+        if args.gather == "p2p":                      # slots stored straight into every rank's buffer over NVLink peer memory
+            peer = rdist.PeerGather(dist, pairs, slot)
+        else:
+            rdist.init_nccl_from_torch(dist)
+            send = rdist.DeviceBuffer(slot * pairs)
+            recv = rdist.DeviceBuffer(slot * pairs * world)
 
     def step():
         r = st.encode_consecutive(F, 3.0)
-        if world > 1:
+        if peer is not None:
+            peer.exchange(st)
+        elif world > 1:
             cabi.check(L.rbf_stream_allgather_bitmaps(st._h, pairs, slot, send.ptr, recv.ptr), ctx)
         return r
 
@@ -294,6 +299,16 @@ def run_ours(args):
     cabi.check(L.rbf_timer_stop_ms(ctx, C.byref(ms)), ctx)
     launches = int(L.rbf_get_counter(ctx, b"kernel_launches"))
     barrier()
+    gather_check = None
+    if world > 1 and args.verify_gather:              # outside the timed region: what arrived is what the owners hold
+        import hashlib
+        got = peer.result() if peer is not None else recv.to_host().reshape(world, pairs, slot)
+        mine = [hashlib.sha256(got[rank, t].tobytes()).hexdigest() for t in range(pairs)]
+        own = [hashlib.sha256(np.pad(st.fetch(t, want_mask=False)[0], (0, slot))[:slot].tobytes()).hexdigest() for t in range(pairs)]
+        table = [None] * world
+        dist.all_gather_object(table, own)
+        gather_check = all(hashlib.sha256(got[r, t].tobytes()).hexdigest() == table[r][t] for r in range(world) for t in range(pairs))
+        gather_check = bool(gather_check and mine == own)
     ms_local = ms.value
     if dist is not None:
         import torch
@@ -351,7 +366,7 @@ def run_ours(args):
             "config": {"workload": "4K (3840x2160) YUV444 %d-frame synthetic stream -> %d inter-frame pairs per GPU, p=0.05, "
                                    "threshold=3.0, seeds 0x12345678/0x87654321/999 (BASELINE configs[2]%s)" %
                                    (F, pairs, "; frames sharded per rank + one NCCL all-gather of the bit arrays" if world > 1 else ""),
-                       "height": H, "width": W, "frames": F, "pairs_per_gpu": pairs, "parallelism": "frame-sharded x%d" % world,
+                       "height": H, "width": W, "frames": F, "pairs_per_gpu": pairs, "parallelism": "frame-sharded x%d" % world, "gather": (args.gather if world > 1 else None), "gather_verified": gather_check,
                        "l2_policy": "inputs larger than L2: %.2f GB of frames per step, no flush needed" % (F * n * 3 / 1e9),
                        "k1_variant": "tma-bulk-ring" if args.k1_variant == 1 else "ldg256", "rank_bound_to_gpu_numa_node": numa_bound,
                        "query_variant": {0: "per-lane", 1: "staged-rings", 2: "staged-rings+dsmem-cluster", 3: "dense-A+B", 4: "decade-tiles"}.get(args.query_variant),
@@ -401,6 +416,8 @@ def main():
     ap.add_argument("--k1-variant", type=int, default=0)
     ap.add_argument("--query-variant", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"], help="N > 1: ncclAllGather, or the library's peer-memory push kernel")
+    ap.add_argument("--verify-gather", action="store_true", help="N > 1: after the timed region compare every received slot with its owner's bit array")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

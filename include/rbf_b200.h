@@ -189,6 +189,23 @@ int rbf_nccl_allgather(rbf_ctx* ctx, const void* d_send, void* d_recv, uint64_t 
 int rbf_stream_allgather_bitmaps(rbf_stream* s, uint32_t pairs, uint64_t slot_bytes, void* d_send, void* d_recv);
 int rbf_nccl_destroy(rbf_ctx* ctx);
 
+/* The same exchange without NCCL on the data path: every rank maps the receive buffers and flag arrays of all ranks
+ * (CUDA IPC; the 64-byte handles travel over the caller's channel, like the NCCL id) and
+ * rbf_stream_allgather_bitmaps becomes ONE kernel that stores this rank's slots straight into every rank's
+ * receive buffer over NVLink, followed by a system-scope release of a sequence number into each rank's flag array.
+ *   receive buffer: 2 halves x nranks x pairs x slot_bytes (cudaMalloc via rbf_malloc); exchange number q lands in
+ *   half q & 1 (rbf_peer_gather_half), so a rank may still read exchange q-1 while its peers deliver q;
+ *   flag array: nranks uint32, zeroed by its owner before the handles are exchanged.
+ * All ranks must use the same pairs and slot_bytes.  As with the NCCL form the call only enqueues work; the other
+ * ranks' slots are complete after rbf_sync / rbf_timer_stop_ms / rbf_memcpy_d2h, which return an error if a peer
+ * did not deliver within ~3 s instead of hanging. */
+int rbf_peer_export(rbf_ctx* ctx, const void* d_ptr, uint8_t handle_out[64]);
+int rbf_peer_open(rbf_ctx* ctx, const uint8_t handle[64], void** d_ptr_out);
+int rbf_peer_close(rbf_ctx* ctx, void* d_ptr);
+int rbf_peer_gather_init(rbf_ctx* ctx, int rank, int nranks, void* const* recv_ptrs, void* const* flag_ptrs);
+int rbf_peer_gather_half(rbf_ctx* ctx, uint32_t* half_out);
+int rbf_peer_gather_shutdown(rbf_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

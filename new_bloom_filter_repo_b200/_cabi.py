@@ -49,6 +49,7 @@ EXPORTS = [
     "rbf_stream_encode_host", "rbf_stream_fetch", "rbf_stream_decode_verify", "rbf_stream_bitmap_region", "rbf_stream_stage_ms",
     "rbf_stream_gather_changed", "rbf_stream_apply_diff", "rbf_stream_download", "rbf_median_blur5", "rbf_stream_median5",
     "rbf_nccl_unique_id", "rbf_nccl_init", "rbf_nccl_allgather", "rbf_stream_allgather_bitmaps", "rbf_nccl_destroy",
+    "rbf_peer_export", "rbf_peer_open", "rbf_peer_close", "rbf_peer_gather_init", "rbf_peer_gather_half", "rbf_peer_gather_shutdown",
 ]
 
 
@@ -120,6 +121,12 @@ def _sig(L):
     L.rbf_nccl_allgather.argtypes = [vp, vp, vp, u64]
     L.rbf_stream_allgather_bitmaps.argtypes = [vp, u32, u64, vp, vp]
     L.rbf_nccl_destroy.argtypes = [vp]
+    L.rbf_peer_export.argtypes = [vp, vp, vp]
+    L.rbf_peer_open.argtypes = [vp, vp, P(vp)]
+    L.rbf_peer_close.argtypes = [vp, vp]
+    L.rbf_peer_gather_init.argtypes = [vp, i32, i32, P(vp), P(vp)]
+    L.rbf_peer_gather_half.argtypes = [vp, P(u32)]
+    L.rbf_peer_gather_shutdown.argtypes = [vp]
 
 
 def lib():

@@ -28,6 +28,13 @@ struct rbf_ctx {
     cudaStream_t st_comm = nullptr;   // slot packing + ncclAllGather of rbf_stream_allgather_bitmaps (overlaps the next encode)
     cudaEvent_t ev_enc = nullptr, ev_pack = nullptr, ev_comm = nullptr;
     bool pack_pending = false, comm_pending = false;
+    // exchange over NVLink peer memory (rbf_peer_gather_init): receive buffers / flag arrays of all ranks as mapped here
+    int peer_nranks = 0, peer_rank = 0;
+    uint32_t* peer_recv[16] = {nullptr};
+    uint32_t* peer_flags[16] = {nullptr};
+    uint32_t peer_seq = 0;
+    bool peer_wait_pending = false;
+    uint32_t* peer_err = nullptr;     // mapped pinned word, set by k_peer_wait on time-out
     int host_chunk_frames = 32;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaDeviceProp prop;
@@ -223,6 +230,7 @@ extern "C" void rbf_ctx_destroy(rbf_ctx* c) {
     if (c->ev_enc) cudaEventDestroy(c->ev_enc);
     if (c->ev_pack) cudaEventDestroy(c->ev_pack);
     if (c->ev_comm) cudaEventDestroy(c->ev_comm);
+    if (c->peer_err) cudaFreeHost(c->peer_err);
     delete c;
 }
 extern "C" const char* rbf_last_error(const rbf_ctx* c) { return c ? c->err : g_err; }
@@ -265,15 +273,27 @@ static int wait_pack(rbf_ctx* c) {
     return RBF_OK;
 }
 // make the context's stream wait for an all-gather still running on the communication stream
+static const long long kPeerTimeoutCycles = 6000000000LL;    // ~3 s of SM clocks: a lost peer must not hang the GPU
 static int join_comm(rbf_ctx* c) {
     if (c->comm_pending) { CK(c, cudaStreamWaitEvent(c->st, c->ev_comm, 0)); c->comm_pending = false; c->pack_pending = false; }
+    if (c->peer_wait_pending) {                                // the other ranks' slots of the last exchange
+        LAUNCH(c, launch_peer_wait(c->peer_flags[c->peer_rank], c->peer_nranks, c->peer_seq, kPeerTimeoutCycles, c->peer_err, c->st));
+        c->peer_wait_pending = false;
+    }
+    return RBF_OK;
+}
+static int check_peer_err(rbf_ctx* c) {                        // call after the stream has been synchronised
+    if (c->peer_err && *(volatile uint32_t*)c->peer_err) {
+        *(volatile uint32_t*)c->peer_err = 0;
+        return set_err(c, RBF_ERR_NCCL, "peer exchange timed out: a rank did not deliver its slots");
+    }
     return RBF_OK;
 }
 extern "C" int rbf_sync(rbf_ctx* c) {
     if (!c) return RBF_ERR_INVALID;
     if (int r = join_comm(c)) return r;
     CK(c, cudaStreamSynchronize(c->st));
-    return RBF_OK;
+    return check_peer_err(c);
 }
 extern "C" int rbf_timer_start(rbf_ctx* c) { if (!c) return RBF_ERR_INVALID; CK(c, cudaEventRecord(c->ev0, c->st)); return RBF_OK; }
 extern "C" int rbf_timer_stop_ms(rbf_ctx* c, double* ms) {
@@ -284,7 +304,7 @@ extern "C" int rbf_timer_stop_ms(rbf_ctx* c, double* ms) {
     float f = 0;
     CK(c, cudaEventElapsedTime(&f, c->ev0, c->ev1));
     *ms = f;
-    return RBF_OK;
+    return check_peer_err(c);
 }
 
 // memory
@@ -299,7 +319,8 @@ extern "C" int rbf_memcpy_h2d(rbf_ctx* c, void* d, const void* h, size_t n) {
 extern "C" int rbf_memcpy_d2h(rbf_ctx* c, void* h, const void* d, size_t n) {
     if (!c) return RBF_ERR_INVALID;
     if (int r = join_comm(c)) return r;
-    CK(c, cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c->st)); CK(c, cudaStreamSynchronize(c->st)); c->d2h += n; return RBF_OK;
+    CK(c, cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c->st)); CK(c, cudaStreamSynchronize(c->st)); c->d2h += n;
+    return check_peer_err(c);
 }
 extern "C" int rbf_memset(rbf_ctx* c, void* d, int v, size_t n) { if (!c) return RBF_ERR_INVALID; CK(c, cudaMemsetAsync(d, v, n, c->st)); return RBF_OK; }
 
@@ -1049,18 +1070,45 @@ extern "C" int rbf_nccl_allgather(rbf_ctx* c, const void* d_send, void* d_recv, 
 // Packs the bit arrays of the last encode into fixed-size slots and all-gathers them on the context's communication
 // stream: the call returns once the work is enqueued, the next rbf_stream_encode overlaps it (it only waits for the
 // packing before it clears the bit arrays).  d_recv is complete after rbf_sync, rbf_timer_stop_ms or rbf_memcpy_d2h.
-extern "C" int rbf_stream_allgather_bitmaps(rbf_stream* s, uint32_t pairs, uint64_t slot_bytes, void* d_send, void* d_recv) {
-    if (!s || !d_send || !d_recv) return set_err(s ? s->c : nullptr, RBF_ERR_INVALID, "rbf_stream_allgather_bitmaps: NULL");
-    rbf_ctx* c = s->c;
-    const size_t stride = s->mask_stride_w * 4;
-    if (slot_bytes == 0 || slot_bytes > stride || pairs > s->max_pairs) return set_err(c, RBF_ERR_INVALID, "bad slot/pairs");
-    if (!c->nccl_comm) return set_err(c, RBF_ERR_STATE, "rbf_stream_allgather_bitmaps: communicator not initialised");
+static int ensure_comm_stream(rbf_ctx* c) {
     if (!c->st_comm) {
         CK(c, cudaStreamCreateWithFlags(&c->st_comm, cudaStreamNonBlocking));
         CK(c, cudaEventCreateWithFlags(&c->ev_enc, cudaEventDisableTiming));
         CK(c, cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
         CK(c, cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
     }
+    return RBF_OK;
+}
+extern "C" int rbf_stream_allgather_bitmaps(rbf_stream* s, uint32_t pairs, uint64_t slot_bytes, void* d_send, void* d_recv) {
+    if (!s || !d_recv) return set_err(s ? s->c : nullptr, RBF_ERR_INVALID, "rbf_stream_allgather_bitmaps: NULL");
+    rbf_ctx* c = s->c;
+    const size_t stride = s->mask_stride_w * 4;
+    if (slot_bytes == 0 || slot_bytes > stride || (slot_bytes & 3) || pairs == 0 || pairs > s->max_pairs)
+        return set_err(c, RBF_ERR_INVALID, "bad slot/pairs");
+    if (c->peer_nranks > 0) {
+        // peer-memory exchange: one kernel stores this rank's slots into every rank's receive buffer over NVLink
+        if (d_recv != (void*)c->peer_recv[c->peer_rank]) return set_err(c, RBF_ERR_INVALID, "d_recv is not the buffer given to rbf_peer_gather_init");
+        if (int r = ensure_comm_stream(c)) return r;
+        CK(c, cudaEventRecord(c->ev_enc, c->st));                   // the encode that produced the bit arrays
+        CK(c, cudaStreamWaitEvent(c->st_comm, c->ev_enc, 0));
+        // every rank has signalled the previous exchange => it has consumed the one before it: that half is free everywhere
+        if (c->peer_seq > 0)
+            LAUNCH(c, launch_peer_wait(c->peer_flags[c->peer_rank], c->peer_nranks, c->peer_seq, kPeerTimeoutCycles, c->peer_err, c->st_comm));
+        c->peer_seq++;
+        const uint32_t slot_w = (uint32_t)(slot_bytes / 4);
+        const size_t half_w = (size_t)c->peer_nranks * pairs * slot_w;
+        const size_t dst_off_w = (size_t)(c->peer_seq & 1u) * half_w + (size_t)c->peer_rank * pairs * slot_w;
+        LAUNCH(c, launch_push_slots(s->d_bits, s->mask_stride_w, slot_w, pairs, c->peer_recv, c->peer_flags, c->peer_nranks, c->peer_rank,
+                                    dst_off_w, c->peer_seq, c->sm_count, c->st_comm));
+        c->launches++;                                              // push + signal
+        CK(c, cudaEventRecord(c->ev_pack, c->st_comm));
+        CK(c, cudaEventRecord(c->ev_comm, c->st_comm));
+        c->pack_pending = c->comm_pending = c->peer_wait_pending = true;
+        return RBF_OK;
+    }
+    if (!d_send) return set_err(c, RBF_ERR_INVALID, "rbf_stream_allgather_bitmaps: d_send is NULL");
+    if (!c->nccl_comm) return set_err(c, RBF_ERR_STATE, "rbf_stream_allgather_bitmaps: communicator not initialised");
+    if (int r = ensure_comm_stream(c)) return r;
     CK(c, cudaEventRecord(c->ev_enc, c->st));                       // the encode that produced the bit arrays
     CK(c, cudaStreamWaitEvent(c->st_comm, c->ev_enc, 0));
     CK(c, cudaMemcpy2DAsync(d_send, slot_bytes, s->d_bits, stride, slot_bytes, pairs, cudaMemcpyDeviceToDevice, c->st_comm));
@@ -1069,6 +1117,62 @@ extern "C" int rbf_stream_allgather_bitmaps(rbf_stream* s, uint32_t pairs, uint6
     if (int r = nccl_allgather_on(c, d_send, d_recv, slot_bytes * pairs, c->st_comm)) return r;
     CK(c, cudaEventRecord(c->ev_comm, c->st_comm));
     c->comm_pending = true;
+    return RBF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// exchange over NVLink peer memory: CUDA IPC handles travel over the caller's channel (like the NCCL id)
+// ------------------------------------------------------------------------------------------
+extern "C" int rbf_peer_export(rbf_ctx* c, const void* d_ptr, uint8_t handle_out[64]) {
+    if (!c || !d_ptr || !handle_out) return set_err(c, RBF_ERR_INVALID, "rbf_peer_export: NULL");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CK(c, cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+    memcpy(handle_out, &h, 64);
+    return RBF_OK;
+}
+extern "C" int rbf_peer_open(rbf_ctx* c, const uint8_t handle[64], void** d_out) {
+    if (!c || !handle || !d_out) return set_err(c, RBF_ERR_INVALID, "rbf_peer_open: NULL");
+    CK(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(c, cudaIpcOpenMemHandle(d_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return RBF_OK;
+}
+extern "C" int rbf_peer_close(rbf_ctx* c, void* d_ptr) {
+    if (!c) return RBF_ERR_INVALID;
+    if (d_ptr) CK(c, cudaIpcCloseMemHandle(d_ptr));
+    return RBF_OK;
+}
+extern "C" int rbf_peer_gather_init(rbf_ctx* c, int rank, int nranks, void* const* recv_ptrs, void* const* flag_ptrs) {
+    if (!c || !recv_ptrs || !flag_ptrs) return set_err(c, RBF_ERR_INVALID, "rbf_peer_gather_init: NULL");
+    if (nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks) return set_err(c, RBF_ERR_INVALID, "rank %d of %d", rank, nranks);
+    for (int r = 0; r < nranks; r++)
+        if (!recv_ptrs[r] || !flag_ptrs[r]) return set_err(c, RBF_ERR_INVALID, "rbf_peer_gather_init: pointer of rank %d is NULL", r);
+    CK(c, cudaSetDevice(c->device));
+    if (!c->peer_err) {
+        CK(c, cudaHostAlloc((void**)&c->peer_err, 64, cudaHostAllocMapped));
+        *c->peer_err = 0;
+    }
+    for (int r = 0; r < 16; r++) {
+        c->peer_recv[r] = r < nranks ? (uint32_t*)recv_ptrs[r] : nullptr;
+        c->peer_flags[r] = r < nranks ? (uint32_t*)flag_ptrs[r] : nullptr;
+    }
+    c->peer_rank = rank; c->peer_nranks = nranks; c->peer_seq = 0; c->peer_wait_pending = false;
+    return RBF_OK;
+}
+extern "C" int rbf_peer_gather_half(rbf_ctx* c, uint32_t* half_out) {
+    if (!c || !half_out) return RBF_ERR_INVALID;
+    if (c->peer_nranks == 0 || c->peer_seq == 0) return set_err(c, RBF_ERR_STATE, "no peer exchange has run");
+    *half_out = c->peer_seq & 1u;
+    return RBF_OK;
+}
+extern "C" int rbf_peer_gather_shutdown(rbf_ctx* c) {
+    if (!c) return RBF_ERR_INVALID;
+    if (c->st_comm) CK(c, cudaStreamSynchronize(c->st_comm));
+    if (c->st) CK(c, cudaStreamSynchronize(c->st));
+    c->peer_nranks = 0; c->peer_seq = 0; c->peer_wait_pending = false; c->comm_pending = c->pack_pending = false;
     return RBF_OK;
 }
 extern "C" int rbf_nccl_destroy(rbf_ctx* c) {

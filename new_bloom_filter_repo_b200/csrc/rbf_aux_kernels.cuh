@@ -185,3 +185,50 @@ __global__ void k_hash_debug(const uint32_t* __restrict__ items, uint32_t count,
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// Multi-GPU exchange over NVLink peer memory: instead of packing the bit arrays into a send buffer
+// and handing it to ncclAllGather, ONE kernel reads each pair's bit array once and stores its slot straight into
+// the receive buffer of every rank (peer pointers obtained through CUDA IPC; plain st.global to a peer address is an
+// NVLink write).  Completion is a per-source sequence number stored with system-scope release into each rank's flag
+// array; the consumer spins on its LOCAL flags with acquire loads (bounded, so a lost peer cannot hang the GPU).
+// ------------------------------------------------------------------------------------------
+constexpr int PEER_MAX = 16;
+struct PeerTable {
+    uint32_t* recv[PEER_MAX];      // receive buffer of rank r as mapped in THIS process (own entry: the local buffer)
+    uint32_t* flags[PEER_MAX];     // flag array of rank r (one uint32 per source rank)
+};
+
+__global__ void __launch_bounds__(256) k_push_slots(const uint32_t* __restrict__ bits, size_t stride_w, uint32_t slot_w, uint32_t pairs,
+                                                    PeerTable pt, int nranks, size_t dst_off_w) {
+    const size_t total = (size_t)pairs * slot_w;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t pair = (uint32_t)(i / slot_w), w = (uint32_t)(i - (size_t)pair * slot_w);
+        const uint32_t v = __ldg(bits + (size_t)pair * stride_w + w);
+#pragma unroll 1
+        for (int r = 0; r < nranks; r++) pt.recv[r][dst_off_w + i] = v;
+    }
+}
+// after k_push_slots on the same stream: tell every rank that this rank's slots of exchange `seq` have landed
+__global__ void k_peer_signal(PeerTable pt, int nranks, int rank, uint32_t seq) {
+    const int r = threadIdx.x;
+    if (r < nranks) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pt.flags[r] + rank), "r"(seq) : "memory");
+    }
+}
+// wait until every source rank has signalled exchange `seq` (sequence numbers only grow); *err = 1 on time-out
+__global__ void k_peer_wait(const uint32_t* __restrict__ flags, int nranks, uint32_t seq, long long timeout_cycles, uint32_t* err) {
+    const int r = threadIdx.x;
+    if (r < nranks) {
+        const long long t0 = clock64();
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+            if ((int32_t)(v - seq) >= 0) break;
+            if (clock64() - t0 > timeout_cycles) { *err = 1u; break; }
+            __nanosleep(200);
+        } while (true);
+    }
+    __threadfence_system();
+}

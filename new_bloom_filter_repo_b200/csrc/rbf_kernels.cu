@@ -355,4 +355,22 @@ cudaError_t launch_hash_debug(const uint32_t* d_items, uint32_t count, uint64_t 
     return cudaGetLastError();
 }
 
+cudaError_t launch_push_slots(const uint32_t* d_bits, size_t stride_w, uint32_t slot_w, uint32_t pairs, uint32_t* const* recv,
+                              uint32_t* const* flags, int nranks, int rank, size_t dst_off_w, uint32_t seq, int sm_count, cudaStream_t st) {
+    if (nranks < 1 || nranks > PEER_MAX) return cudaErrorInvalidValue;
+    PeerTable pt;
+    for (int r = 0; r < PEER_MAX; r++) { pt.recv[r] = r < nranks ? recv[r] : nullptr; pt.flags[r] = r < nranks ? flags[r] : nullptr; }
+    const size_t total = (size_t)pairs * slot_w;
+    size_t grid = (total + 255) / 256;
+    if (grid > (size_t)sm_count * 8) grid = (size_t)sm_count * 8;
+    if (grid < 1) grid = 1;
+    k_push_slots<<<(unsigned)grid, 256, 0, st>>>(d_bits, stride_w, slot_w, pairs, pt, nranks, dst_off_w);
+    k_peer_signal<<<1, 32, 0, st>>>(pt, nranks, rank, seq);
+    return cudaGetLastError();
+}
+cudaError_t launch_peer_wait(const uint32_t* d_flags, int nranks, uint32_t seq, long long timeout_cycles, uint32_t* d_err, cudaStream_t st) {
+    k_peer_wait<<<1, 32, 0, st>>>(d_flags, nranks, seq, timeout_cycles, d_err);
+    return cudaGetLastError();
+}
+
 }  // namespace rbf

@@ -75,6 +75,11 @@ cudaError_t launch_items_str(const FrameJob* d_job, const uint8_t* d_blob, const
 cudaError_t launch_hash_debug(const uint32_t* d_items, uint32_t count, uint64_t seed, uint64_t* d_out, int mode,
                               cudaStream_t st);
 
+// exchange over peer memory: store `pairs` slots of slot_w words into recv[r] + dst_off_w of every rank, then signal `seq`
+cudaError_t launch_push_slots(const uint32_t* d_bits, size_t stride_w, uint32_t slot_w, uint32_t pairs, uint32_t* const* recv,
+                              uint32_t* const* flags, int nranks, int rank, size_t dst_off_w, uint32_t seq, int sm_count, cudaStream_t st);
+cudaError_t launch_peer_wait(const uint32_t* d_flags, int nranks, uint32_t seq, long long timeout_cycles, uint32_t* d_err, cudaStream_t st);
+
 int query_max_smem_bytes();
 
 }  // namespace rbf

@@ -2,8 +2,10 @@
 Multi-GPU plumbing: one process per GPU.  Inter-frame pairs are independent units
 (BloomFilterCompressor.compress keeps no state between frames, ivc:198-266), so ranks take
 contiguous blocks of pairs (each block needs one halo frame: its first `prev`) and the only
-exchange is ONE ncclAllGather of the packed Bloom bit arrays.  torch.distributed is used for the
-rendezvous only (broadcast of the NCCL unique id, barriers, max-over-ranks timing).
+exchange is ONE all-gather of the packed Bloom bit arrays: either ncclAllGather, or (PeerGather) a
+kernel of the library that stores the slots straight into every rank's receive buffer over NVLink
+peer memory.  torch.distributed is used for the rendezvous only (NCCL unique id / CUDA IPC handles,
+barriers, max-over-ranks timing).
 """
 from __future__ import annotations
 
@@ -80,3 +82,63 @@ def allgather_bitmaps(stream, pairs: int, slot_bytes: int, world: int):
     recv = DeviceBuffer(slot_bytes * pairs * world)
     _cabi.check(_cabi.lib().rbf_stream_allgather_bitmaps(stream._h, pairs, slot_bytes, send.ptr, recv.ptr), _cabi.ctx())
     return send, recv
+
+
+class PeerGather:
+    """Receive buffers of all ranks mapped into this process (CUDA IPC) so that rbf_stream_allgather_bitmaps becomes one
+    kernel writing over NVLink.  Layout of `recv`: [half 0|1][rank][pair][slot_bytes]; `result()` returns the half that
+    holds the last exchange as uint8[world, pairs, slot]."""
+
+    def __init__(self, dist, pairs: int, slot_bytes: int):
+        L, ctx = _cabi.lib(), _cabi.ctx()
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.pairs, self.slot = int(pairs), int(slot_bytes)
+        self.recv = DeviceBuffer(2 * self.world * self.pairs * self.slot)
+        self.flags = DeviceBuffer(256)
+        _cabi.check(L.rbf_memset(ctx, self.flags.ptr, 0, 256), ctx)
+        _cabi.check(L.rbf_sync(ctx), ctx)
+        mine = np.zeros((2, 64), dtype=np.uint8)
+        self._opened = []
+        recv_ptrs, flag_ptrs = (C.c_void_p * self.world)(), (C.c_void_p * self.world)()
+        if self.world > 1:
+            _cabi.check(L.rbf_peer_export(ctx, self.recv.ptr, _cabi.ptr(mine[0])), ctx)
+            _cabi.check(L.rbf_peer_export(ctx, self.flags.ptr, _cabi.ptr(mine[1])), ctx)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine.tobytes())
+            for r in range(self.world):
+                if r == self.rank:
+                    recv_ptrs[r], flag_ptrs[r] = self.recv.ptr.value, self.flags.ptr.value
+                    continue
+                h = np.frombuffer(handles[r], dtype=np.uint8).reshape(2, 64).copy()
+                pr, pf = C.c_void_p(), C.c_void_p()
+                _cabi.check(L.rbf_peer_open(ctx, _cabi.ptr(h[0]), C.byref(pr)), ctx)
+                _cabi.check(L.rbf_peer_open(ctx, _cabi.ptr(h[1]), C.byref(pf)), ctx)
+                self._opened += [pr, pf]
+                recv_ptrs[r], flag_ptrs[r] = pr.value, pf.value
+        else:
+            recv_ptrs[0], flag_ptrs[0] = self.recv.ptr.value, self.flags.ptr.value
+        _cabi.check(L.rbf_peer_gather_init(ctx, self.rank, self.world, recv_ptrs, flag_ptrs), ctx)
+        if dist is not None:
+            dist.barrier()                                  # nobody pushes before every rank has mapped and zeroed
+
+    def exchange(self, stream) -> None:
+        """Enqueue the push of the last encode's bit arrays (overlaps the next encode; complete after rbf_sync)."""
+        _cabi.check(_cabi.lib().rbf_stream_allgather_bitmaps(stream._h, self.pairs, self.slot, None, self.recv.ptr), _cabi.ctx())
+
+    def result(self) -> np.ndarray:
+        half = C.c_uint32()
+        _cabi.check(_cabi.lib().rbf_sync(_cabi.ctx()), _cabi.ctx())
+        _cabi.check(_cabi.lib().rbf_peer_gather_half(_cabi.ctx(), C.byref(half)), _cabi.ctx())
+        n = self.world * self.pairs * self.slot
+        return self.recv.to_host()[half.value * n:(half.value + 1) * n].reshape(self.world, self.pairs, self.slot)
+
+    def close(self, dist=None) -> None:
+        L, ctx = _cabi.lib(), _cabi.ctx()
+        L.rbf_peer_gather_shutdown(ctx)
+        if dist is not None:
+            dist.barrier()                                  # peers may still be writing into this rank's buffers
+        for p in self._opened:
+            L.rbf_peer_close(ctx, p)
+        self._opened = []
+        self.recv.free(); self.flags.free()

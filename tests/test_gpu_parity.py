@@ -2,6 +2,7 @@
 against (i) the golden fixtures generated from the real reference and (ii) the oracle on the
 same seeded inputs.  Integer / bit work: every comparison is bit-exact."""
 import math
+import os
 import random
 
 import numpy as np
@@ -517,4 +518,37 @@ def test_median5_resident_frame_matches_cv2(pkg):
     out = np.empty((270, 481), np.uint8)
     pkg._cabi.check(pkg._cabi.lib().rbf_stream_median5(st._h, 1, pkg._cabi.ptr(out)), pkg._cabi.ctx())
     assert np.array_equal(out, cv2.medianBlur(np.ascontiguousarray(frames[1][:, :, 0]), 5))
+    st.close()
+
+
+# ------------------------------------------------------------------ exchange over peer memory (single rank here; N > 1: bench.py --gather p2p --verify-gather)
+@pytest.mark.skipif(os.environ.get("RBF_TEST_PEER") != "1",
+                    reason="peer-memory exchange is opt-in until it has been validated on a multi-GPU box (RBF_TEST_PEER=1)")
+def test_peer_gather_single_rank(pkg):
+    from new_bloom_filter_repo_b200 import distributed as rdist
+    cabi = pkg._cabi
+    st = pkg.FrameStream(270, 480, 3, np.uint8, max_frames=5)
+    st.upload(synth_stream(270, 480, 5, 41, [0.05, 0.1]))
+    res = st.encode_consecutive(5, 3.0)
+    slot = (max((r.l + 7) // 8 for r in res) + 15) // 16 * 16 + 64
+    pg = rdist.PeerGather(None, 4, slot)
+    try:
+        want1 = [st.fetch(t, want_mask=False)[0] for t in range(4)]
+        pg.exchange(st)
+        st.upload(synth_stream(270, 480, 5, 43, [0.1, 0.05]))      # the push overlaps this encode and must not see it
+        st.encode_consecutive(5, 3.0)
+        got1 = pg.result()
+        assert got1.shape == (1, 4, slot)
+        for t in range(4):
+            assert np.array_equal(got1[0, t, : len(want1[t])], want1[t]) and not got1[0, t, len(want1[t]):].any()
+        want2 = [st.fetch(t, want_mask=False)[0] for t in range(4)]
+        pg.exchange(st)
+        got2 = pg.result()                                       # the other half of the receive buffer
+        for t in range(4):
+            assert np.array_equal(got2[0, t, : len(want2[t])], want2[t])
+        full = pg.recv.to_host().reshape(2, 1, 4, slot)
+        for t in range(4):                                       # exchange 1 is still intact in half 1
+            assert np.array_equal(full[1, 0, t, : len(want1[t])], want1[t])
+    finally:
+        pg.close()
     st.close()
