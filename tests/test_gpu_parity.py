@@ -156,6 +156,28 @@ def test_query_kernel_variants_vs_oracle(pkg, co, variant, n, p_gen, seed):
         L.rbf_set_option(ctx, b"query_variant", 4)
 
 
+@pytest.mark.parametrize("variant", [0, 1, 3, 4])
+@pytest.mark.parametrize("k,l", [(3.5, 16), (2.2, 5), (3.0, 64), (1.0, 7), (2.999, 2), (3.4, 40000)])
+def test_query_saturated_filter_and_empty_regions(pkg, co, variant, k, l):
+    """A tiny (saturated) Bloom array makes every position survive every stage -- the survivor buffers and the stage-C ring
+    of the compacting kernels run full -- and the second half of the mask is empty, so whole slabs have no member to skip."""
+    L, ctx = pkg._cabi.lib(), pkg._cabi.ctx()
+    n = 150000
+    rng = np.random.default_rng(77)
+    m = np.zeros(n, dtype=np.uint8)
+    m[: n // 3] = rng.random(n // 3) < 0.15
+    ob, ow, *_ = co.compress(m, k_l_override=(k, l))
+    pkg._cabi.check(L.rbf_set_option(ctx, b"query_variant", variant), ctx)
+    try:
+        comp = pkg.BloomFilterCompressor()
+        bitmap, witness, p, nn, ratio = comp.compress(m, k_l_override=(k, l))
+        assert len(bitmap) == l and np.array_equal(bitmap, ob)
+        assert np.array_equal(np.array(witness, dtype=np.uint8), ow)
+        assert np.array_equal(comp.decompress(bitmap, witness, n, k), m)
+    finally:
+        L.rbf_set_option(ctx, b"query_variant", 4)
+
+
 def test_decompress_short_witness_raises(pkg):
     m = mask_for({"n": 5000, "p_gen": 0.05, "seed": 3})
     comp = pkg.BloomFilterCompressor()
