@@ -130,10 +130,74 @@ def _cpu_worker(args):
 
 
 def host_cores() -> int:
+    """CPUs this process may really use: min(affinity mask, cpuset.cpus.effective, ceil(cpu.max quota / period)).
+    A container lease often shows all of the box's CPUs in the affinity mask while its CFS quota is far smaller; a pool
+    sized from the mask then thrashes (5.8 vs 34 Mpx/s for the same port on "128 cores")."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    def _read(*paths):
+        for q in paths:
+            try:
+                with open(q) as f:
+                    return f.read().strip()
+            except OSError:
+                continue
+        return None
+    eff = _read("/sys/fs/cgroup/cpuset.cpus.effective", "/sys/fs/cgroup/cpuset/cpuset.effective_cpus")
+    if eff:
+        cnt = 0
+        for part in eff.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cnt += int(b) - int(a) + 1
+            elif part:
+                cnt += 1
+        if cnt:
+            n = min(n, cnt)
+    mx = _read("/sys/fs/cgroup/cpu.max")
+    if mx:
+        f = mx.split()
+        if len(f) == 2 and f[0] != "max":
+            n = min(n, max(1, -(-int(f[0]) // int(f[1]))))
+    else:
+        q, per = _read("/sys/fs/cgroup/cpu/cpu.cfs_quota_us"), _read("/sys/fs/cgroup/cpu/cpu.cfs_period_us")
+        if q and per and int(q) > 0:
+            n = min(n, max(1, -(-int(q) // int(per))))
+    return max(1, n)
+
+
+def _spin(n):
+    t0 = time.perf_counter()
+    x = 0
+    for i in range(n):
+        x += i * i
+    return time.perf_counter() - t0
+
+
+def effective_cores(limit: int) -> float:
+    """Measured parallelism: a fixed pure-Python spin on 1 process vs on `limit` processes at once.  Catches CPU quotas the
+    cgroup files do not show (effective = limit * t_single / t_parallel)."""
+    import multiprocessing as mp
+    if limit <= 1:
+        return 1.0
+    n = 6000000                                                            # ~0.25 s of CPython per task
+    with mp.get_context("fork").Pool(limit) as pool:
+        pool.map(_spin, [1000] * limit, chunksize=1)                      # start-up
+        t1 = min(pool.map(_spin, [n], chunksize=1)[0] for _ in range(2))
+        t0 = time.perf_counter()
+        pool.map(_spin, [n] * limit, chunksize=1)
+        tp = time.perf_counter() - t0
+    return max(1.0, min(float(limit), limit * t1 / tp))
+
+
+def reference_pool_size():
+    """-> (workers, note).  One worker per usable core: cgroup/affinity limit, cut down to the measured parallelism."""
+    lim = host_cores()
+    eff = effective_cores(lim)
+    use = max(1, min(lim, int(round(eff))))
+    return use, "affinity/cgroup limit %d, measured parallelism %.1f" % (lim, eff)
 
 
 class CpuReferencePool:
@@ -155,6 +219,16 @@ class CpuReferencePool:
         wall = time.perf_counter() - t0
         px = sum(r[1] for r in res)
         return px / wall / 1e6, px, wall
+
+    def full_frame_check(self, height: int, width: int, tasks: int, seed: int = 777):
+        """Calibration of the band sample: `tasks` FULL frames (n = height*width, 7-digit indices like the GPU workload)
+        through the same port, one per worker -> Mpx/s per core at full-frame n."""
+        tasks = max(1, min(tasks, self.cores))
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, [(seed + i, height, width) for i in range(tasks)], chunksize=1)
+        wall = time.perf_counter() - t0
+        per_core = float(np.mean([r[1] / r[2] / 1e6 for r in res]))
+        return {"n": height * width, "tasks": tasks, "wall_s": wall, "mpx_per_core": per_core}
 
     def close(self):
         self.pool.close()
@@ -178,11 +252,11 @@ def cpu_c_oracle_sample(cores: int, frames: np.ndarray):
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's own CPU path (ported loop for loop) on all host cores."""
+    """`--impl reference`: the reference's own CPU path (ported loop for loop) on all usable host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    use = host_cores()
+    use, note = reference_pool_size()
     rows = 68                                   # 68 x 3840 = 261 120 px per task: ~0.4 s of reference Python
     pool = CpuReferencePool(use)
     vals = []
@@ -190,6 +264,7 @@ def run_reference(args):
         mps, px, wall = pool.sample(1, rows, args.width, seed=5000 + 100 * i)
         if i >= args.warmup:
             vals.append((mps, px, wall))
+    ffc = pool.full_frame_check(args.height, args.width, 2) if args.full_frame_check else None
     pool.close()
     value = float(np.mean([v[0] for v in vals]))
     ms = float(np.mean([v[2] for v in vals]) * 1e3)
@@ -199,7 +274,8 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": "4K (3840x2160) YUV444 inter-frame stream, p=0.05, threshold=3.0; bounded sample: " + sample},
-            "cpu_baseline": {"value": value, "unit": "Mpixels/s", "cores": use, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": "Mpixels/s", "cores": use, "mpx_per_core": value / use, "kind": "port",
+                             "cores_note": note, "full_frame_check": ffc,
                              "sample": sample + "; " + ref_port.HASH_IMPL},
             "e2e": {"value": value, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -233,6 +309,53 @@ def bind_near_gpu(gpu_index: int) -> bool:
         return False
 
 
+def stream_frames(F, H, W, seed, lo, hi, out):
+    """Frames [lo, hi] of fill_stream(F-frame stream, seed) written to out[0 .. hi-lo] without building the whole stream:
+    frame t = frame 0 + sum of the deltas 1..t (uint8 arithmetic wraps, so the sum may be taken in any order)."""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    base = ((yy * 3 + xx * 2) % 240).astype(np.uint8)
+    f0 = np.empty((H, W, 3), dtype=np.uint8)
+    f0[:, :, 0] = base
+    f0[:, :, 1] = base // 2 + 7
+    f0[:, :, 2] = base // 3 + 90
+    f0 += rng.integers(0, 8, (H, W, 3), dtype=np.uint8)
+
+    def delta(t):
+        r = np.random.default_rng(seed + t)
+        return (r.integers(0, 20, (H, W), dtype=np.uint8) == 0).view(np.uint8) * np.uint8(64)
+
+    workers = max(1, min(16, (os.cpu_count() or 2) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
+    acc = np.zeros((H, W), dtype=np.uint8)
+    with ThreadPoolExecutor(workers) as ex:
+        for t0 in range(1, lo + 1, 32):                    # fold the deltas before the shard into one offset
+            for d in ex.map(delta, range(t0, min(lo + 1, t0 + 32))):
+                acc += d
+        np.add(f0, acc[:, :, None], out=out[0])
+        for t0 in range(lo + 1, hi + 1, 32):
+            ts = list(range(t0, min(hi + 1, t0 + 32)))
+            for t, d in zip(ts, ex.map(delta, ts)):
+                np.add(out[t - lo - 1], d[:, :, None], out=out[t - lo])
+
+
+def kernel_counters(qkernel: str):
+    """Per-pair ncu counters of the query kernel (profiles/r02_<kernel>_counters.json, written by scripts/ncu_summary.py
+    from an `ncu --set full` capture of THIS round), valid only while the kernel sources still hash to what was profiled."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_%s_counters.json" % qkernel)) as f:
+            c = json.load(f)
+        h = hashlib.sha256()
+        for name in c.get("sources", []):
+            with open(os.path.join(ROOT, name), "rb") as f:
+                h.update(f.read())
+        c["stale"] = h.hexdigest()[:16] != c.get("sources_sha16")
+        return c
+    except Exception:
+        return None
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,19 +366,31 @@ def run_ours(args):
         import torch.distributed as dist                 # rendezvous / barriers only; the data path is the library's NCCL
         dist.init_process_group(backend="gloo")
         numa_bound = bind_near_gpu(local)
+    import hashlib
     import new_bloom_filter_repo_b200 as pkg
     from new_bloom_filter_repo_b200 import _cabi as cabi, distributed as rdist
     L, ctx = cabi.lib(), cabi.ctx()
     info = cabi.device_info()
     H, W, F = args.height, args.width, args.frames
     n = H * W
-    pairs = F - 1
+    strong = args.scaling == "strong" and world > 1
     cabi.check(L.rbf_set_option(ctx, b"k1_variant", args.k1_variant), ctx)
     cabi.check(L.rbf_set_option(ctx, b"query_variant", args.query_variant), ctx)
+    if args.ranges is not None:
+        cabi.check(L.rbf_set_option(ctx, b"encode_ranges", args.ranges), ctx)
 
-    frames, pin = pinned_array(cabi, (F, H, W, 3))
-    fill_stream(frames, seed=3 + 1000 * rank)
-    st = pkg.FrameStream(H, W, 3, np.uint8, max_frames=F)
+    if strong:                                            # ONE stream of F frames, contiguous blocks of pairs per rank + halo frame
+        lo, hi = rdist.shard_pairs(F - 1, rank, world)
+        pairs = hi - lo
+        slots_per_rank = -(-(F - 1) // world)             # every rank contributes the same number of slots
+        nfr = pairs + 1
+        frames, pin = pinned_array(cabi, (nfr, H, W, 3))
+        stream_frames(F, H, W, 3, lo, hi, frames)
+    else:                                                 # weak: one F-frame stream per rank
+        lo, pairs, slots_per_rank, nfr = 0, F - 1, F - 1, F
+        frames, pin = pinned_array(cabi, (F, H, W, 3))
+        fill_stream(frames, seed=3 + 1000 * rank)
+    st = pkg.FrameStream(H, W, 3, np.uint8, max_frames=nfr, max_pairs=max(pairs, slots_per_rank))
     st.upload(frames)
 
     def barrier():
@@ -266,22 +401,22 @@ def run_ours(args):
     # multi-GPU: one all-gather of the packed bit arrays per step
     send = recv = peer = None
     slot = 0
-    res = st.encode_consecutive(F, 3.0)
+    res = st.encode_consecutive(nfr, 3.0)
     if world > 1:
         slot = rdist.agree_slot_bytes(dist, max(r.l for r in res))
         if args.gather == "p2p":                      # slots stored straight into every rank's buffer over NVLink peer memory
-            peer = rdist.PeerGather(dist, pairs, slot)
+            peer = rdist.PeerGather(dist, slots_per_rank, slot)
         else:
             rdist.init_nccl_from_torch(dist)
-            send = rdist.DeviceBuffer(slot * pairs)
-            recv = rdist.DeviceBuffer(slot * pairs * world)
+            send = rdist.DeviceBuffer(slot * slots_per_rank)
+            recv = rdist.DeviceBuffer(slot * slots_per_rank * world)
 
     def step():
-        r = st.encode_consecutive(F, 3.0)
+        r = st.encode_consecutive(nfr, 3.0)
         if peer is not None:
             peer.exchange(st)
         elif world > 1:
-            cabi.check(L.rbf_stream_allgather_bitmaps(st._h, pairs, slot, send.ptr, recv.ptr), ctx)
+            cabi.check(L.rbf_stream_allgather_bitmaps(st._h, slots_per_rank, slot, send.ptr, recv.ptr), ctx)
         return r
 
     sampler = ClockSampler(local)
@@ -299,16 +434,38 @@ def run_ours(args):
     cabi.check(L.rbf_timer_stop_ms(ctx, C.byref(ms)), ctx)
     launches = int(L.rbf_get_counter(ctx, b"kernel_launches"))
     barrier()
-    gather_check = None
-    if world > 1 and args.verify_gather:              # outside the timed region: what arrived is what the owners hold
-        import hashlib
-        got = peer.result() if peer is not None else recv.to_host().reshape(world, pairs, slot)
-        mine = [hashlib.sha256(got[rank, t].tobytes()).hexdigest() for t in range(pairs)]
-        own = [hashlib.sha256(np.pad(st.fetch(t, want_mask=False)[0], (0, slot))[:slot].tobytes()).hexdigest() for t in range(pairs)]
+
+    # ---- outside the timed region: what was timed is checked
+    # (1) every pair decodes back to its mask on the GPU (ivc:268-307 round trip)
+    mism = st.decode_verify()
+    roundtrip_ok = not bool(mism.any())
+    own_bm = [st.fetch(t, want_mask=False) for t in range(pairs)]
+    # (2) N > 1: every received slot equals the owner's bit array
+    gather_check = strong_check = None
+    if world > 1 and args.verify_gather:
+        got = peer.result() if peer is not None else recv.to_host().reshape(world, slots_per_rank, slot)
+        own = [hashlib.sha256(np.pad(own_bm[t][0], (0, slot))[:slot].tobytes()).hexdigest() for t in range(pairs)]
         table = [None] * world
         dist.all_gather_object(table, own)
-        gather_check = all(hashlib.sha256(got[r, t].tobytes()).hexdigest() == table[r][t] for r in range(world) for t in range(pairs))
-        gather_check = bool(gather_check and mine == own)
+        gather_check = all(hashlib.sha256(got[r, t].tobytes()).hexdigest() == table[r][t]
+                           for r in range(world) for t in range(len(table[r])))
+        gather_check = bool(gather_check and [hashlib.sha256(got[rank, t].tobytes()).hexdigest() for t in range(pairs)] == own)
+        flags = [None] * world
+        dist.all_gather_object(flags, gather_check)
+        gather_check = all(flags)
+        if strong and rank == 0:                      # (3) the gathered set == a single-GPU encode of the same F-frame stream
+            full = np.empty((F, H, W, 3), dtype=np.uint8)
+            fill_stream(full, seed=3)
+            st1 = pkg.FrameStream(H, W, 3, np.uint8, max_frames=F)
+            st1.upload(full)
+            r1 = st1.encode_consecutive(F, 3.0)
+            flat = [got[r, t] for r in range(world) for t in range(len(table[r]))]
+            strong_check = len(flat) == F - 1
+            for t in range(F - 1):
+                bm1 = st1.fetch(t, want_mask=False)[0]
+                strong_check = strong_check and bool(np.array_equal(np.pad(bm1, (0, slot))[:slot], flat[t]))
+            st1.close()
+            del full
     ms_local = ms.value
     if dist is not None:
         import torch
@@ -318,7 +475,7 @@ def run_ours(args):
     else:
         ms_total = ms_local
     ms_per_step = ms_total / args.steps
-    total_px = pairs * n * world
+    total_px = (F - 1) * n if strong else pairs * n * world
     value = total_px / (ms_per_step * 1e-3) / 1e6
     stage = {k_: v / args.steps for k_, v in stage_acc.items()}
 
@@ -327,8 +484,10 @@ def run_ours(args):
     wt_slot = (max((r.wlen + 7) // 8 for r in res) + 15) // 16 * 16
     out_bm, pin_bm = pinned_array(cabi, (pairs, bm_slot))
     out_wt, pin_wt = pinned_array(cabi, (pairs, wt_slot))
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, args.e2e_steps)
     st.encode_host(frames, 3.0, bitmap_slot=bm_slot, witness_slot=wt_slot, out_bitmaps=out_bm, out_witness=out_wt)
+    e2e_ok = all(np.array_equal(out_bm[t, :own_bm[t][0].size], own_bm[t][0]) and
+                 np.array_equal(out_wt[t, :own_bm[t][1].size], own_bm[t][1]) for t in range(pairs))
     barrier()
     cabi.check(L.rbf_reset_counters(ctx), ctx)
     cabi.check(L.rbf_timer_start(ctx), ctx)
@@ -347,27 +506,56 @@ def run_ours(args):
     e2e_value = total_px / (e2e_ms * 1e-3) / 1e6
     clocks = sampler.stop()            # sampled from the first warm-up step to the end of the e2e region
 
+    # a plain pinned H2D copy of the same frames: what the link itself gives this rank (the e2e ceiling)
+    cabi.check(L.rbf_sync(ctx), ctx)
+    t0 = time.perf_counter()
+    st.upload(frames)
+    pcie_peak = frames.nbytes / (time.perf_counter() - t0) / 1e9
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         q_ms = stage["k3_query"]
         coded_px = sum(r.n for r in res if not r.raw)
-        traffic = None
         qkernel = "k_query3" if args.query_variant == 4 else "k_query2"
-        try:                                     # dram bytes per launch of the query kernel from the committed ncu --set full capture
-            with open(os.path.join(ROOT, "profiles", "r01_%s_traffic.json" % qkernel)) as f:
-                traffic = json.load(f)["dram_bytes_per_pair"] * sum(1 for r in res if not r.raw)
-        except Exception:
-            pass
+        kc = kernel_counters(qkernel)
+        traffic = issue_frac = inst_px = None
+        if kc is not None and not kc["stale"]:
+            ncoded = sum(1 for r in res if not r.raw)
+            traffic = kc["dram_bytes_per_pair"] * ncoded
+            issue_frac, inst_px = kc.get("issue_active_frac"), kc.get("thread_inst_per_px")
         achieved = coded_px * BYTES_PER_PIXEL / (q_ms * 1e-3) / 1e9
+        # (4) bitmap + witness of three pairs against the C oracle on the same frames
+        oracle_ok = None
+        if not args.no_cpu:
+            from concurrent.futures import ThreadPoolExecutor
+            from oracle import c_oracle as co
+
+            def against_oracle(t):
+                m, ones = co.frame_diff_mask(frames[t], frames[t + 1], 3.0)
+                ob, ow, *_rest = co.compress(m.reshape(-1))
+                return (ones == res[t].ones and np.array_equal(own_bm[t][0], np.packbits(ob)) and
+                        np.array_equal(own_bm[t][1], np.packbits(ow)))
+            picks = sorted({0, pairs // 2, pairs - 1})
+            with ThreadPoolExecutor(len(picks)) as ex:
+                oracle_ok = all(ex.map(against_oracle, picks))
+        parity = bool(roundtrip_ok and e2e_ok and (oracle_ok is not False) and (gather_check is not False) and
+                      (strong_check is not False))
         line = {
             "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic",
-            "config": {"workload": "4K (3840x2160) YUV444 %d-frame synthetic stream -> %d inter-frame pairs per GPU, p=0.05, "
-                                   "threshold=3.0, seeds 0x12345678/0x87654321/999 (BASELINE configs[2]%s)" %
-                                   (F, pairs, "; frames sharded per rank + one NCCL all-gather of the bit arrays" if world > 1 else ""),
-                       "height": H, "width": W, "frames": F, "pairs_per_gpu": pairs, "parallelism": "frame-sharded x%d" % world, "gather": (args.gather if world > 1 else None), "gather_verified": gather_check,
-                       "l2_policy": "inputs larger than L2: %.2f GB of frames per step, no flush needed" % (F * n * 3 / 1e9),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "4K (3840x2160) YUV444 %d-frame synthetic stream -> %s, p=0.05, "
+                                   "threshold=3.0, seeds 0x12345678/0x87654321/999 (BASELINE configs[%s]%s)" %
+                                   (F, ("%d inter-frame pairs block-partitioned over %d GPUs (%d on rank 0)" % (F - 1, world, pairs)) if strong
+                                    else "%d inter-frame pairs per GPU" % pairs, "3" if strong else "2",
+                                    "; frames sharded per rank + one all-gather of the bit arrays" if world > 1 else ""),
+                       "height": H, "width": W, "frames": F, "pairs_per_gpu": pairs, "parallelism": "frame-sharded x%d" % world,
+                       "gather": (args.gather if world > 1 else None), "gather_verified": gather_check,
+                       "strong_matches_single_gpu": strong_check,
+                       "parity_checked": parity,
+                       "parity": {"decode_roundtrip_all_pairs": roundtrip_ok, "e2e_outputs_equal_resident": bool(e2e_ok),
+                                  "c_oracle_pairs_0_mid_last": oracle_ok},
+                       "l2_policy": "inputs larger than L2: %.2f GB of frames per step, no flush needed" % (nfr * n * 3 / 1e9),
                        "k1_variant": "tma-bulk-ring" if args.k1_variant == 1 else "ldg256", "rank_bound_to_gpu_numa_node": numa_bound,
                        "query_variant": {0: "per-lane", 1: "staged-rings", 2: "staged-rings+dsmem-cluster", 3: "dense-A+B", 4: "decade-tiles"}.get(args.query_variant),
                        "mean_l_bits": float(np.mean([r.l for r in res])), "mean_witness_bits": float(np.mean([r.wlen for r in res]))},
@@ -375,24 +563,30 @@ def run_ours(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": coded_px * BYTES_PER_PIXEL, "launch_ms": q_ms,
                          "pipeline_frac": value * 1e6 * BYTES_PER_PIXEL / 1e9 / world / peak,
+                         "issue_frac": issue_frac, "thread_inst_per_px": inst_px,
+                         "counters_source": (None if kc is None else ("profiles/r02_%s_counters.json%s" % (qkernel, " (STALE: kernel sources changed)" if kc["stale"] else ""))),
+                         "note": "6 B/px counts both frames of a pair; consecutive pairs share a frame through L2, DRAM traffic of K1 is ~3.2 B/px",
                          "stage_ms": stage},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "rbf_stream_encode_host (pinned host frames in, packed "
-                    "bitmaps + witnesses out)"},
+                    "ms_per_step": e2e_ms, "steps": e2e_steps, "pcie_gbs": (h2d + d2h) / (e2e_ms * 1e-3) / 1e9,
+                    "pcie_h2d_copy_gbs": pcie_peak, "pcie_frac_of_plain_copy": h2d / (e2e_ms * 1e-3) / 1e9 / pcie_peak,
+                    "api": "rbf_stream_encode_host (pinned host frames in, packed bitmaps + witnesses out)"},
             "gpu_launches": launches,
             "device": info["name"],
         }
         if world == 1 and not args.no_cpu:
-            use = host_cores()
+            use, note = reference_pool_size()
             pool = CpuReferencePool(use)
             mps, px, wall = pool.sample(8, 68, W)
+            ffc = pool.full_frame_check(H, W, 2) if args.full_frame_check else None
             pool.close()
-            line["cpu_baseline"] = {"value": mps, "unit": "Mpixels/s", "cores": use, "kind": "port",
+            line["cpu_baseline"] = {"value": mps, "unit": "Mpixels/s", "cores": use, "mpx_per_core": mps / use, "kind": "port",
+                                    "cores_note": note, "full_frame_check": ffc,
                                     "sample": "%d bands of 68x%d px (8 per core, p=0.05) through oracle/ref_port.py in %.1f s"
                                               % (8 * use, W, wall)}
             try:
-                cm, cn = cpu_c_oracle_sample(use, frames[: min(F, use + 1)])
+                cm, cn = cpu_c_oracle_sample(use, frames[: min(nfr, use + 1)])
                 line["cpu_baseline_c_oracle"] = {"value": cm, "unit": "Mpixels/s", "cores": cn, "kind": "port",
                                                  "sample": "%d full 4K pairs, one per thread, oracle/rbf_oracle.c" % cn}
             except Exception as e:       # pragma: no cover
@@ -417,7 +611,17 @@ def main():
     ap.add_argument("--query-variant", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"], help="N > 1: ncclAllGather, or the library's peer-memory push kernel")
-    ap.add_argument("--verify-gather", action="store_true", help="N > 1: after the timed region compare every received slot with its owner's bit array")
+    ap.add_argument("--no-verify-gather", dest="verify_gather", action="store_false",
+                    help="N > 1: skip the post-run comparison of every received slot with its owner's bit array")
+    ap.add_argument("--verify-gather", dest="verify_gather", action="store_true", help="(default) kept for compatibility")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = one --frames stream per rank; strong = ONE --frames stream block-partitioned over the ranks "
+                         "(BASELINE configs[3]), every rank ends up with all bit arrays, rank 0 re-encodes the stream alone and compares")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--ranges", type=int, default=None, help="split each encode into this many pipelined ranges (library default if unset)")
+    ap.add_argument("--no-full-frame-check", dest="full_frame_check", action="store_false",
+                    help="CPU baseline: skip the full-frame (n = H*W) calibration sample")
+    ap.set_defaults(verify_gather=True, full_frame_check=True)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RBF_ABI_VERSION 1
+#define RBF_ABI_VERSION 2
 
 typedef enum {
     RBF_OK = 0,
@@ -73,7 +73,10 @@ void rbf_ctx_destroy(rbf_ctx* ctx);
 const char* rbf_last_error(const rbf_ctx* ctx);
 int rbf_device_info(rbf_ctx* ctx, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor,
                     uint64_t* total_mem_bytes);
-/* options: "k1_variant" (0 = vectorised loads, 1 = TMA bulk-copy ring), "query_smem_bytes" (cap) */
+/* options: "k1_variant" (0 = vectorised loads, 1 = TMA bulk-copy ring), "query_smem_bytes" (cap), "query_variant",
+ * "insert_variant", "host_chunk_frames", "encode_ranges" (1..8: K1/K2 pipelining depth of rbf_stream_encode),
+ * "k1_ctas_per_sm" / "pipe_k1_ctas_per_sm" (K1 grid caps); "k1_only" / "mask_mode" here are only the defaults that
+ * streams created afterwards inherit -- per-stream state lives in rbf_stream_set_option. */
 int rbf_set_option(rbf_ctx* ctx, const char* key, int64_t value);
 int64_t rbf_get_counter(rbf_ctx* ctx, const char* key);   /* "kernel_launches", "h2d_bytes", "d2h_bytes" */
 int rbf_reset_counters(rbf_ctx* ctx);
@@ -139,6 +142,13 @@ int rbf_decompress_mask(rbf_ctx* ctx, const uint8_t* bitmap_unpacked, uint64_t l
 int rbf_stream_create(rbf_ctx* ctx, uint32_t height, uint32_t width, uint32_t channels, uint32_t sample_bytes,
                       uint32_t max_frames, uint32_t max_pairs, rbf_stream** out);
 void rbf_stream_destroy(rbf_stream* s);
+/* per-stream options (no process-global state: two compressors in one process do not interfere):
+ *   "k1_only"   1: rbf_stream_encode stops after K1 (mask + counts) -- VideoFrameCompressor._calculate_frame_diff (ivc:784-808);
+ *               infos report wlen = 0 and rbf_stream_fetch refuses bitmap / witness pointers
+ *   "mask_mode" 0: |dY| > threshold (ivc:808); 1: additionally any byte of the pixel differs (lossless GOP mode)
+ *   "gray_mode" 1: 3-channel frames are BGR and the mask is taken on cv2.cvtColor(.., COLOR_BGR2GRAY) (ivc:792-795),
+ *               OpenCV's fixed point (3735 B + 19235 G + 9798 R + 16384) >> 15 for 8- and 16-bit samples */
+int rbf_stream_set_option(rbf_stream* s, const char* key, int64_t value);
 int rbf_stream_upload(rbf_stream* s, uint32_t first_frame, uint32_t count, const void* host_frames);
 int rbf_stream_frame_ptr(rbf_stream* s, uint32_t frame, void** dptr);
 /* threshold: the Python float compared with `diff > threshold` (ivc:808).  k_override/l_override: NULL or [pairs]. */
@@ -152,13 +162,20 @@ int rbf_stream_encode_host(rbf_stream* s, const void* host_frames, uint32_t nfra
  * mask as little-bit-order packed bytes (ceil(n/8)); any pointer may be NULL */
 int rbf_stream_fetch(rbf_stream* s, uint32_t pair, uint8_t* bitmap_packbits, uint8_t* witness_packbits,
                      uint8_t* mask_packed_little);
+/* the same for pairs [first, first+count) at once: output k of a kind lands at base + k*slot_bytes (slot_bytes bytes are copied
+ * per pair, capped at the device slot); one synchronisation for the whole batch.  NULL pointers are skipped. */
+int rbf_stream_fetch_batch(rbf_stream* s, uint32_t first, uint32_t count, uint8_t* bitmaps_packbits, uint64_t bitmap_slot_bytes,
+                           uint8_t* witness_packbits, uint64_t witness_slot_bytes, uint8_t* masks_packed_little,
+                           uint64_t mask_slot_bytes);
 /* decode the pairs encoded by the last rbf_stream_encode from their own bitmap + witness (ivc:268-307) and
  * compare with the stored masks on the device: mismatches_out[pair] = differing mask words */
 int rbf_stream_decode_verify(rbf_stream* s, uint32_t pairs, uint64_t* mismatches_out);
 int rbf_stream_bitmap_region(rbf_stream* s, void** dptr, uint64_t* stride_bytes);
-/* device time (CUDA events) of the stages of the last rbf_stream_encode:
- * out = { K1 threshold, host round trip + job upload + memsets, K2 insert, K3 query, K3b witness } in ms */
-int rbf_stream_stage_ms(rbf_stream* s, double out[5]);
+/* device time (CUDA events) of the stages of the last rbf_stream_encode, ms.  K1 and K2 are pipelined over ranges of pairs
+ * on two streams, so their spans overlap:
+ * out = { K1 span, everything in front of K3 (K1 + host (k,l,T) round trips + K2 as overlapped), K2 span, K3 query,
+ *         K3b witness, whole encode } */
+int rbf_stream_stage_ms(rbf_stream* s, double out[6]);
 
 /* ---- SURVEY 8(f) rows N1 / N2, device side
  * N1  changed-value gather of VideoFrameCompressor._calculate_frame_diff (ivc:810-842): for each pair of the last

@@ -32,6 +32,7 @@ class MaskInfo(C.Structure):
                 ("floor_k", C.c_uint32), ("raw", C.c_uint32)]
 
 
+ABI_VERSION = 2
 IVC_SEEDS = (0x12345678, 0x87654321, 999)    # improved_video_compressor.py:62-63,94
 BC_SEEDS = (0, 1, 999)                       # bloom_compress.py:163-164,195
 
@@ -45,8 +46,8 @@ EXPORTS = [
     "rbf_filter_create", "rbf_filter_destroy", "rbf_filter_add_indices", "rbf_filter_check_indices",
     "rbf_filter_add_strings", "rbf_filter_check_strings", "rbf_filter_get_bits", "rbf_filter_set_bits",
     "rbf_compress_mask", "rbf_decompress_mask",
-    "rbf_stream_create", "rbf_stream_destroy", "rbf_stream_upload", "rbf_stream_frame_ptr", "rbf_stream_encode",
-    "rbf_stream_encode_host", "rbf_stream_fetch", "rbf_stream_decode_verify", "rbf_stream_bitmap_region", "rbf_stream_stage_ms",
+    "rbf_stream_create", "rbf_stream_destroy", "rbf_stream_set_option", "rbf_stream_upload", "rbf_stream_frame_ptr", "rbf_stream_encode",
+    "rbf_stream_encode_host", "rbf_stream_fetch", "rbf_stream_fetch_batch", "rbf_stream_decode_verify", "rbf_stream_bitmap_region", "rbf_stream_stage_ms",
     "rbf_stream_gather_changed", "rbf_stream_apply_diff", "rbf_stream_download", "rbf_median_blur5", "rbf_stream_median5",
     "rbf_nccl_unique_id", "rbf_nccl_init", "rbf_nccl_allgather", "rbf_stream_allgather_bitmaps", "rbf_nccl_destroy",
     "rbf_peer_export", "rbf_peer_open", "rbf_peer_close", "rbf_peer_gather_init", "rbf_peer_gather_half", "rbf_peer_gather_shutdown",
@@ -103,11 +104,13 @@ def _sig(L):
     L.rbf_stream_create.argtypes = [vp, u32, u32, u32, u32, u32, u32, P(vp)]
     L.rbf_stream_destroy.argtypes = [vp]
     L.rbf_stream_destroy.restype = None
+    L.rbf_stream_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.rbf_stream_upload.argtypes = [vp, u32, u32, vp]
     L.rbf_stream_frame_ptr.argtypes = [vp, u32, P(vp)]
     L.rbf_stream_encode.argtypes = [vp, vp, vp, u32, dbl, P(Seeds), vp, vp, vp]
     L.rbf_stream_encode_host.argtypes = [vp, vp, u32, dbl, P(Seeds), vp, vp, u64, vp, u64]
     L.rbf_stream_fetch.argtypes = [vp, u32, vp, vp, vp]
+    L.rbf_stream_fetch_batch.argtypes = [vp, u32, u32, vp, u64, vp, u64, vp, u64]
     L.rbf_stream_decode_verify.argtypes = [vp, u32, vp]
     L.rbf_stream_bitmap_region.argtypes = [vp, P(vp), P(u64)]
     L.rbf_stream_stage_ms.argtypes = [vp, vp]
@@ -140,7 +143,7 @@ def lib():
                                    "this package has no CPU fallback")
                 L = C.CDLL(SO_PATH)
                 _sig(L)
-                if L.rbf_abi_version() != 1:
+                if L.rbf_abi_version() != ABI_VERSION:
                     raise RbfError("ABI version mismatch")
                 _lib = L
     return _lib
@@ -163,7 +166,7 @@ def ctx():
                 h = C.c_void_p()
                 check(lib().rbf_ctx_create(dev, C.byref(h)))
                 _ctx = h
-                for key in ("query_variant", "insert_variant", "k1_variant"):      # experiment knobs, e.g. RBF_QUERY_VARIANT=4
+                for key in ("query_variant", "insert_variant", "k1_variant", "encode_ranges", "pipe_k1_ctas_per_sm"):      # experiment knobs, e.g. RBF_QUERY_VARIANT=4
                     val = os.environ.get("RBF_" + key.upper())
                     if val is not None:
                         check(lib().rbf_set_option(h, key.encode(), int(val)), h)

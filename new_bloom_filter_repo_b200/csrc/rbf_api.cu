@@ -36,6 +36,12 @@ struct rbf_ctx {
     bool peer_wait_pending = false;
     uint32_t* peer_err = nullptr;     // mapped pinned word, set by k_peer_wait on time-out
     int host_chunk_frames = 32;
+    cudaStream_t st_k1 = nullptr;     // pipelined encode: K1 of the later ranges + the witness memset run here, beside K2 on `st`
+    cudaStream_t st_d2h = nullptr;    // rbf_stream_encode_host: result copies of chunk i overlap the kernels of chunk i+1
+    cudaEvent_t ev_fork = nullptr, ev_wit = nullptr, ev_k1[8] = {nullptr}, ev_d2h = nullptr;
+    int encode_ranges = 4;            // rbf_stream_encode: K1/K2 pipelined over this many ranges of pairs (1 = serial)
+    int k1_ctas_per_sm = 32;          // grid cap of K1 (pipelined encodes use pipe_k1_ctas_per_sm so that K2 finds room beside it)
+    int pipe_k1_ctas_per_sm = 4;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaDeviceProp prop;
     int sm_count = 0;
@@ -225,6 +231,12 @@ extern "C" void rbf_ctx_destroy(rbf_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->st) cudaStreamDestroy(c->st);
+    if (c->st_k1) cudaStreamDestroy(c->st_k1);
+    if (c->st_d2h) cudaStreamDestroy(c->st_d2h);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_wit) cudaEventDestroy(c->ev_wit);
+    if (c->ev_d2h) cudaEventDestroy(c->ev_d2h);
+    for (auto& e : c->ev_k1) if (e) cudaEventDestroy(e);
     if (c->st_copy) cudaStreamDestroy(c->st_copy);
     if (c->st_comm) { cudaStreamSynchronize(c->st_comm); cudaStreamDestroy(c->st_comm); }
     if (c->ev_enc) cudaEventDestroy(c->ev_enc);
@@ -251,8 +263,11 @@ extern "C" int rbf_set_option(rbf_ctx* c, const char* key, int64_t v) {
     if (!strcmp(key, "query_variant")) { c->query_variant = (int)(v < 0 ? 0 : (v > 4 ? 4 : v)); return RBF_OK; }
     if (!strcmp(key, "insert_variant")) { c->insert_variant = v ? 1 : 0; return RBF_OK; }
     if (!strcmp(key, "host_chunk_frames")) { c->host_chunk_frames = (int)v; return RBF_OK; }
-    if (!strcmp(key, "k1_only")) { c->k1_only = v ? 1 : 0; return RBF_OK; }
-    if (!strcmp(key, "mask_mode")) { c->mask_mode = v ? 1 : 0; return RBF_OK; }
+    if (!strcmp(key, "k1_only")) { c->k1_only = v ? 1 : 0; return RBF_OK; }        // default of streams created afterwards
+    if (!strcmp(key, "mask_mode")) { c->mask_mode = v ? 1 : 0; return RBF_OK; }    // (per-stream: rbf_stream_set_option)
+    if (!strcmp(key, "encode_ranges")) { c->encode_ranges = (int)(v < 1 ? 1 : (v > 8 ? 8 : v)); return RBF_OK; }
+    if (!strcmp(key, "k1_ctas_per_sm")) { c->k1_ctas_per_sm = (int)(v < 1 ? 1 : (v > 64 ? 64 : v)); return RBF_OK; }
+    if (!strcmp(key, "pipe_k1_ctas_per_sm")) { c->pipe_k1_ctas_per_sm = (int)(v < 1 ? 1 : (v > 64 ? 64 : v)); return RBF_OK; }
     if (!strcmp(key, "query_smem_bytes")) {
         c->query_smem_cap = (int)((v <= 0 || v > query_max_smem_bytes()) ? query_max_smem_bytes() : v);
         return RBF_OK;
@@ -570,6 +585,13 @@ struct rbf_stream {
     uint32_t last_pairs = 0, last_max_l = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool staged = false;
+    // per-stream options (rbf_stream_set_option); defaults come from the context at creation
+    int k1_only = 0;        // stop after K1 (mask + counts): VideoFrameCompressor._calculate_frame_diff
+    int mask_mode = 0;      // 0: |dY| > thr (ivc:808); 1: additionally any byte of the pixel differs
+    int gray_mode = 0;      // 1: the mask is taken on cv2.COLOR_BGR2GRAY of the pixel (ivc:792-795) instead of on sample 0
+    bool last_k1_only = false;
+    size_t bits_hwm = 0, wit_hwm = 0;   // bytes per slot that may hold set bits (see stream_clear_outputs)
+    bool wit_dirty_full = false;
     std::vector<cudaEvent_t> ev_copy;
     std::vector<rbf_mask_info> last_infos;
 };
@@ -624,10 +646,27 @@ extern "C" int rbf_stream_create(rbf_ctx* c, uint32_t H, uint32_t W, uint32_t C,
         return set_err(c, e == cudaErrorMemoryAllocation ? RBF_ERR_OOM : RBF_ERR_CUDA, "rbf_stream_create: %s", cudaGetErrorString(e));
     }
     for (auto& ev : s->ev) CK(c, cudaEventCreate(&ev));
+    memset(s->h_ones, 0, 4 * (size_t)max_pairs); memset(s->h_resid, 0, 4 * (size_t)max_pairs); memset(s->h_wlen, 0, 4 * (size_t)max_pairs);
+    s->k1_only = c->k1_only; s->mask_mode = c->mask_mode;
+    CK(c, cudaMemsetAsync(s->d_wlen, 0, 4 * (size_t)max_pairs, c->st));
+    CK(c, cudaMemsetAsync(s->d_bits, 0, s->mask_stride_w * 4 * max_pairs, c->st));
+    CK(c, cudaMemsetAsync(s->d_wit, 0, s->mask_stride_w * 4 * max_pairs, c->st));
     CK(c, cudaMemsetAsync(s->d_mask, 0, s->mask_stride_w * 4 * max_pairs, c->st));   // zero padding once
     CK(c, cudaStreamSynchronize(c->st));
     *out = s;
     return RBF_OK;
+}
+
+extern "C" int rbf_stream_set_option(rbf_stream* s, const char* key, int64_t v) {
+    if (!s || !key) return set_err(s ? s->c : nullptr, RBF_ERR_INVALID, "rbf_stream_set_option: NULL");
+    if (!strcmp(key, "k1_only")) { s->k1_only = v ? 1 : 0; return RBF_OK; }
+    if (!strcmp(key, "mask_mode")) { s->mask_mode = v ? 1 : 0; return RBF_OK; }
+    if (!strcmp(key, "gray_mode")) {
+        if (v && s->C != 3) return set_err(s->c, RBF_ERR_INVALID, "gray_mode needs 3-channel frames");
+        s->gray_mode = v ? 1 : 0;
+        return RBF_OK;
+    }
+    return set_err(s->c, RBF_ERR_INVALID, "unknown stream option %s", key);
 }
 
 extern "C" int rbf_stream_upload(rbf_stream* s, uint32_t first, uint32_t count, const void* host) {
@@ -660,42 +699,38 @@ static int threshold_to_int(double thr) {
     return (int)floor(thr);
 }
 
-// Encode pairs [first, first+count) (slots of all per-pair arrays); prev_idx/curr_idx are indexed from 0.
-// `pfx` is the slot of this range's century-prefix array (count+1 entries) inside h_prefix/d_prefix.
-static int stream_encode_range(rbf_stream* s, uint32_t first, uint32_t count, uint32_t pfx, const uint32_t* prev_idx,
-                               const uint32_t* curr_idx, double threshold, const rbf_seeds* sd, const double* kov,
-                               const uint64_t* lov, bool record_events) {
-    rbf_ctx* c = s->c;
-    const uint32_t n = (uint32_t)s->npix;
+// ---- pieces of the batched encode ----------------------------------------------------------
+static int stream_thr_int(const rbf_stream* s, double threshold) {
     int thr_int = threshold_to_int(threshold);
-    if (s->S == 2 && threshold < -1.0) {               // int16 abs can be -32768 (ivc:801): keep exact floor
+    if (s->S == 2 && threshold < -1.0)                  // int16 abs can be -32768 (ivc:801): keep exact floor
         thr_int = threshold < -40000.0 ? -40000 : (int)floor(threshold);
-    }
+    return thr_int;
+}
+
+static int stream_fill_pairs(rbf_stream* s, uint32_t first, uint32_t count, const uint32_t* prev_idx, const uint32_t* curr_idx) {
     for (uint32_t i = 0; i < count; i++) {
         if (prev_idx[i] >= s->max_frames || curr_idx[i] >= s->max_frames)
-            return set_err(c, RBF_ERR_INVALID, "pair %u references a frame outside the store", first + i);
+            return set_err(s->c, RBF_ERR_INVALID, "pair %u references a frame outside the store", first + i);
         PairJob& P = s->h_pairs[first + i];
         P.prev = s->d_frames + (size_t)prev_idx[i] * s->frame_stride;
         P.curr = s->d_frames + (size_t)curr_idx[i] * s->frame_stride;
         P.mask = s->d_mask + (size_t)(first + i) * s->mask_stride_w;
     }
-    CK(c, cudaMemcpyAsync(s->d_pairs + first, s->h_pairs + first, sizeof(PairJob) * count, cudaMemcpyHostToDevice, c->st));
-    CK(c, cudaMemsetAsync(s->d_ones + first, 0, 4 * (size_t)count, c->st));
-    CK(c, cudaMemsetAsync(s->d_resid + first, 0, 4 * (size_t)count, c->st));
-    if (record_events) { s->staged = false; CK(c, cudaEventRecord(s->ev[0], c->st)); }
-    LAUNCH(c, launch_threshold(s->d_pairs + first, (int)count, n, (int)s->C, (int)s->S, thr_int, c->mask_mode, s->d_ones + first,
-                               s->d_resid + first, c->k1_variant, c->sm_count, c->st));
-    if (c->k1_variant == 1) c->launches++;              // tail kernel
-    if (record_events) CK(c, cudaEventRecord(s->ev[1], c->st));
-    CK(c, cudaMemcpyAsync(s->h_ones + first, s->d_ones + first, 4 * (size_t)count, cudaMemcpyDeviceToHost, c->st));
-    CK(c, cudaMemcpyAsync(s->h_resid + first, s->d_resid + first, 4 * (size_t)count, cudaMemcpyDeviceToHost, c->st));
-    c->d2h += 8 * (int64_t)count;
-    CK(c, cudaStreamSynchronize(c->st));               // the one host round trip: (p, k, l, T) need libm's log2
-    if (s->last_infos.size() < (size_t)first + count) s->last_infos.resize((size_t)first + count);
-    const uint32_t ncent = (n + 99u) / 100u;
+    return RBF_OK;
+}
+
+struct RangeTotals {
     uint32_t total_cent = 0, coded_pairs = 0, max_l = 0;
-    uint32_t* hp = s->h_prefix + pfx;
-    hp[0] = 0;
+};
+
+// host side of pairs [first, first+count): K1's counts -> (p, k, l, T) exactly as the reference computes them -> FrameJob.
+// hp[i+1] = base_cent + centuries of the coded pairs among the first i+1 of the range (K3's work list).
+static void stream_range_params(rbf_stream* s, uint32_t first, uint32_t count, const rbf_seeds* sd, const double* kov,
+                                const uint64_t* lov, uint32_t* hp, uint32_t base_cent, RangeTotals* out) {
+    const uint32_t n = (uint32_t)s->npix, ncent = (n + 99u) / 100u;
+    if (s->last_infos.size() < (size_t)first + count) s->last_infos.resize((size_t)first + count);
+    uint32_t total_cent = base_cent;
+    hp[0] = base_cent;
     for (uint32_t i = 0; i < count; i++) {
         rbf_mask_info& in = s->last_infos[first + i];
         memset(&in, 0, sizeof in);
@@ -714,27 +749,76 @@ static int stream_encode_range(rbf_stream* s, uint32_t first, uint32_t count, ui
         if (coded) {
             job_set_filter(J, l, k, *sd);
             in.k = k; in.l = l; in.floor_k = J.floor_k; in.act_T = J.act_T;
-            total_cent += ncent; coded_pairs++;
-            if (l > max_l) max_l = (uint32_t)l;
+            total_cent += ncent; out->coded_pairs++;
+            if (l > out->max_l) out->max_l = (uint32_t)l;
         } else {
             in.raw = 1;
         }
         hp[i + 1] = total_cent;
     }
+    out->total_cent = total_cent - base_cent;
+}
+
+// Zero what K2 / K3b will OR into.  Nothing ever writes a bit array at or beyond bit l, or a witness at or beyond bit wlen,
+// and both regions are fully zeroed at creation, so clearing [0, high-water mark) of every slot is enough.
+static int stream_clear_outputs(rbf_stream* s, uint32_t first, uint32_t count, uint32_t max_l, cudaStream_t st) {
+    rbf_ctx* c = s->c;
+    const size_t stride = s->mask_stride_w * 4;
+    const size_t need = align_up((size_t)((max_l + 31u) / 32u) * 4 + 64, 128);
+    if (need > s->bits_hwm) s->bits_hwm = need;
+    const size_t wb = s->bits_hwm < stride ? s->bits_hwm : stride;
+    const size_t ww = (s->wit_dirty_full || s->wit_hwm > stride) ? stride : s->wit_hwm;
+    CK(c, cudaMemset2DAsync(s->d_bits + (size_t)first * s->mask_stride_w, stride, 0, wb, count, st));
+    if (ww) CK(c, cudaMemset2DAsync(s->d_wit + (size_t)first * s->mask_stride_w, stride, 0, ww, count, st));
+    return RBF_OK;
+}
+static void stream_note_witness(rbf_stream* s, uint32_t first, uint32_t count) {      // after the encode has been synchronised
+    for (uint32_t i = 0; i < count; i++) {
+        const size_t nb = align_up((size_t)((s->h_wlen[first + i] + 31u) / 32u) * 4 + 64, 128);
+        if (nb > s->wit_hwm) s->wit_hwm = nb;
+    }
+}
+
+// Encode pairs [first, first+count) (slots of all per-pair arrays) serially on the context's stream; `pfx` is the slot of this
+// range's century-prefix array (count+1 entries) inside h_prefix/d_prefix.  Used per chunk by rbf_stream_encode_host.
+static int stream_encode_range(rbf_stream* s, uint32_t first, uint32_t count, uint32_t pfx, const uint32_t* prev_idx,
+                               const uint32_t* curr_idx, double threshold, const rbf_seeds* sd, const double* kov,
+                               const uint64_t* lov, bool record_events) {
+    rbf_ctx* c = s->c;
+    const uint32_t n = (uint32_t)s->npix;
+    const int thr_int = stream_thr_int(s, threshold);
+    if (int r = stream_fill_pairs(s, first, count, prev_idx, curr_idx)) return r;
+    CK(c, cudaMemcpyAsync(s->d_pairs + first, s->h_pairs + first, sizeof(PairJob) * count, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemsetAsync(s->d_ones + first, 0, 4 * (size_t)count, c->st));
+    CK(c, cudaMemsetAsync(s->d_resid + first, 0, 4 * (size_t)count, c->st));
+    if (record_events) { s->staged = false; CK(c, cudaEventRecord(s->ev[0], c->st)); }
+    LAUNCH(c, launch_threshold(s->d_pairs + first, (int)count, n, (int)s->C, (int)s->S, thr_int, s->mask_mode, s->gray_mode,
+                               s->d_ones + first, s->d_resid + first, c->k1_variant, c->sm_count, c->k1_ctas_per_sm, c->st));
+    if (c->k1_variant == 1 && !s->gray_mode) c->launches++;              // tail kernel
+    if (record_events) CK(c, cudaEventRecord(s->ev[1], c->st));
+    CK(c, cudaMemcpyAsync(s->h_ones + first, s->d_ones + first, 4 * (size_t)count, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaMemcpyAsync(s->h_resid + first, s->d_resid + first, 4 * (size_t)count, cudaMemcpyDeviceToHost, c->st));
+    c->d2h += 8 * (int64_t)count;
+    CK(c, cudaStreamSynchronize(c->st));               // the one host round trip: (p, k, l, T) need libm's log2
+    const uint32_t ncent = (n + 99u) / 100u;
+    RangeTotals rt;
+    uint32_t* hp = s->h_prefix + pfx;
+    stream_range_params(s, first, count, sd, kov, lov, hp, 0, &rt);
     if (first + count > s->last_pairs || first == 0) s->last_pairs = first + count;
-    if (max_l > s->last_max_l || first == 0) s->last_max_l = max_l;
-    if (coded_pairs == 0 || c->k1_only) return RBF_OK;
+    if (rt.max_l > s->last_max_l || first == 0) s->last_max_l = rt.max_l;
+    s->last_k1_only = s->k1_only != 0;
+    if (rt.coded_pairs == 0 || s->k1_only) return RBF_OK;
     CK(c, cudaMemcpyAsync(s->d_jobs + first, s->h_jobs + first, sizeof(FrameJob) * count, cudaMemcpyHostToDevice, c->st));
     CK(c, cudaMemcpyAsync(s->d_prefix + pfx, hp, 4 * ((size_t)count + 1), cudaMemcpyHostToDevice, c->st));
     if (int r = wait_pack(c)) return r;                  // the slots of the last all-gather are packed
-    CK(c, cudaMemsetAsync(s->d_bits + (size_t)first * s->mask_stride_w, 0, s->mask_stride_w * 4 * count, c->st));
-    CK(c, cudaMemsetAsync(s->d_wit + (size_t)first * s->mask_stride_w, 0, s->mask_stride_w * 4 * count, c->st));
+    if (int r = stream_clear_outputs(s, first, count, rt.max_l, c->st)) return r;
     if (record_events) CK(c, cudaEventRecord(s->ev[2], c->st));
     LAUNCH(c, launch_insert(s->d_jobs + first, (int)count, ncent, c->insert_variant, c->sm_count, c->st));
     if (record_events) CK(c, cudaEventRecord(s->ev[3], c->st));
-    LAUNCH(c, launch_query(s->d_jobs + first, s->d_prefix + pfx, (int)count, total_cent, max_l, c->query_variant, c->sm_count,
+    LAUNCH(c, launch_query(s->d_jobs + first, s->d_prefix + pfx, (int)count, rt.total_cent, rt.max_l, c->query_variant, c->sm_count,
                            c->query_smem_cap, c->st));
     if (record_events) CK(c, cudaEventRecord(s->ev[4], c->st));
+    s->wit_dirty_full = true;                            // until the witness lengths of this encode are known
     LAUNCH(c, launch_witness(s->d_jobs + first, (int)count, ncent, c->sm_count, s->d_chunkcnt + 32 * (size_t)first, s->d_wlen + first, c->st));
     c->launches += 2;                                   // pass-count + finalize kernels
     if (record_events) { CK(c, cudaEventRecord(s->ev[5], c->st)); s->staged = true; }
@@ -743,11 +827,91 @@ static int stream_encode_range(rbf_stream* s, uint32_t first, uint32_t count, ui
     return RBF_OK;
 }
 
-static int stream_encode_async(rbf_stream* s, const uint32_t* prev_idx, const uint32_t* curr_idx, uint32_t pairs,
-                               double threshold, const rbf_seeds* sd, const double* kov, const uint64_t* lov) {
+static int ensure_pipe_streams(rbf_ctx* c) {
+    if (!c->st_k1) {
+        CK(c, cudaStreamCreateWithFlags(&c->st_k1, cudaStreamNonBlocking));
+        CK(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        for (auto& e : c->ev_k1) CK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    return RBF_OK;
+}
+
+// The resident-stream encode, pipelined: K1 has no host dependency, so K1 of ALL ranges is enqueued up front on a second
+// stream; as soon as a range's counts have landed the host derives its (k, l, T) and enqueues that range's K2 on the main
+// stream, where it runs BESIDE K1 of the later ranges (K1 is HBM-bound with a grid that leaves SM slots free, K2 is
+// issue/atomics-bound), and the host round trip is hidden behind both.  K3 and K3b are single launches over all pairs.
+static int stream_encode_pipelined(rbf_stream* s, uint32_t pairs, const uint32_t* prev_idx, const uint32_t* curr_idx,
+                                   double threshold, const rbf_seeds* sd, const double* kov, const uint64_t* lov) {
+    rbf_ctx* c = s->c;
+    const uint32_t n = (uint32_t)s->npix, ncent = (n + 99u) / 100u;
+    const int thr_int = stream_thr_int(s, threshold);
+    uint32_t R = (uint32_t)c->encode_ranges;
+    if (R > 8u) R = 8u;
+    if (pairs < 8u * R) R = 1u;                          // small jobs: nothing to hide behind
+    if (int r = ensure_pipe_streams(c)) return r;
+    if (int r = stream_fill_pairs(s, 0, pairs, prev_idx, curr_idx)) return r;
+    CK(c, cudaMemcpyAsync(s->d_pairs, s->h_pairs, sizeof(PairJob) * pairs, cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaMemsetAsync(s->d_ones, 0, 4 * (size_t)pairs, c->st));
+    CK(c, cudaMemsetAsync(s->d_resid, 0, 4 * (size_t)pairs, c->st));
+    s->staged = false;
+    CK(c, cudaEventRecord(s->ev[0], c->st));
+    CK(c, cudaEventRecord(c->ev_fork, c->st));
+    CK(c, cudaStreamWaitEvent(c->st_k1, c->ev_fork, 0));
+    uint32_t lo[9];
+    for (uint32_t r = 0; r <= R; r++) lo[r] = (uint32_t)(((uint64_t)pairs * r) / R);
+    const int k1_cap = R > 1u ? c->pipe_k1_ctas_per_sm : c->k1_ctas_per_sm;
+    for (uint32_t r = 0; r < R; r++) {
+        const uint32_t f = lo[r], cnt = lo[r + 1] - lo[r];
+        LAUNCH(c, launch_threshold(s->d_pairs + f, (int)cnt, n, (int)s->C, (int)s->S, thr_int, s->mask_mode, s->gray_mode, s->d_ones + f,
+                                   s->d_resid + f, c->k1_variant, c->sm_count, k1_cap, c->st_k1));
+        if (c->k1_variant == 1 && !s->gray_mode) c->launches++;
+        CK(c, cudaMemcpyAsync(s->h_ones + f, s->d_ones + f, 4 * (size_t)cnt, cudaMemcpyDeviceToHost, c->st_k1));
+        CK(c, cudaMemcpyAsync(s->h_resid + f, s->d_resid + f, 4 * (size_t)cnt, cudaMemcpyDeviceToHost, c->st_k1));
+        CK(c, cudaEventRecord(c->ev_k1[r], c->st_k1));
+    }
+    CK(c, cudaEventRecord(s->ev[1], c->st_k1));           // end of the last K1
+    c->d2h += 8 * (int64_t)pairs;
     s->last_infos.clear();
-    s->last_pairs = 0; s->last_max_l = 0;
-    return stream_encode_range(s, 0, pairs, 0, prev_idx, curr_idx, threshold, sd, kov, lov, true);
+    s->last_pairs = pairs; s->last_max_l = 0;
+    s->last_k1_only = s->k1_only != 0;
+    RangeTotals all;
+    uint32_t base_cent = 0;
+    bool first_k2 = true;
+    for (uint32_t r = 0; r < R; r++) {
+        const uint32_t f = lo[r], cnt = lo[r + 1] - lo[r];
+        CK(c, cudaEventSynchronize(c->ev_k1[r]));         // this range's counts are on the host
+        RangeTotals rt;
+        stream_range_params(s, f, cnt, sd, kov, lov, s->h_prefix + f, base_cent, &rt);
+        base_cent += rt.total_cent;
+        all.coded_pairs += rt.coded_pairs;
+        if (rt.max_l > all.max_l) all.max_l = rt.max_l;
+        if (s->k1_only || rt.coded_pairs == 0) continue;
+        CK(c, cudaStreamWaitEvent(c->st, c->ev_k1[r], 0)); // K2 reads the masks K1 wrote on the other stream
+        CK(c, cudaMemcpyAsync(s->d_jobs + f, s->h_jobs + f, sizeof(FrameJob) * cnt, cudaMemcpyHostToDevice, c->st));
+        if (first_k2) { if (int e = wait_pack(c)) return e; }
+        if (int e = stream_clear_outputs(s, f, cnt, rt.max_l, c->st)) return e;
+        if (first_k2) { CK(c, cudaEventRecord(s->ev[2], c->st)); first_k2 = false; }
+        LAUNCH(c, launch_insert(s->d_jobs + f, (int)cnt, ncent, c->insert_variant, c->sm_count, c->st));
+    }
+    all.total_cent = base_cent;
+    s->last_max_l = all.max_l;
+    if (s->k1_only || all.coded_pairs == 0) {
+        CK(c, cudaStreamWaitEvent(c->st, c->ev_k1[R - 1], 0));
+        return RBF_OK;
+    }
+    CK(c, cudaMemcpyAsync(s->d_prefix, s->h_prefix, 4 * ((size_t)pairs + 1), cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaEventRecord(s->ev[3], c->st));
+    LAUNCH(c, launch_query(s->d_jobs, s->d_prefix, (int)pairs, all.total_cent, all.max_l, c->query_variant, c->sm_count,
+                           c->query_smem_cap, c->st));
+    CK(c, cudaEventRecord(s->ev[4], c->st));
+    s->wit_dirty_full = true;
+    LAUNCH(c, launch_witness(s->d_jobs, (int)pairs, ncent, c->sm_count, s->d_chunkcnt, s->d_wlen, c->st));
+    c->launches += 2;                                   // pass-count + finalize kernels
+    CK(c, cudaEventRecord(s->ev[5], c->st));
+    s->staged = true;
+    CK(c, cudaMemcpyAsync(s->h_wlen, s->d_wlen, 4 * (size_t)pairs, cudaMemcpyDeviceToHost, c->st));
+    c->d2h += 4 * (int64_t)pairs;
+    return RBF_OK;
 }
 
 extern "C" int rbf_stream_encode(rbf_stream* s, const uint32_t* prev_idx, const uint32_t* curr_idx, uint32_t pairs,
@@ -757,22 +921,30 @@ extern "C" int rbf_stream_encode(rbf_stream* s, const uint32_t* prev_idx, const 
     rbf_ctx* c = s->c;
     if (pairs == 0 || pairs > s->max_pairs) return set_err(c, RBF_ERR_INVALID, "pairs = %u outside [1, %u]", pairs, s->max_pairs);
     CK(c, cudaSetDevice(c->device));
-    int rc = stream_encode_async(s, prev_idx, curr_idx, pairs, threshold, sd, kov, lov);
-    if (rc) return rc;
+    int rc = stream_encode_pipelined(s, pairs, prev_idx, curr_idx, threshold, sd, kov, lov);
+    if (rc) { cudaStreamSynchronize(c->st_k1); cudaStreamSynchronize(c->st); return rc; }
     CK(c, cudaStreamSynchronize(c->st));
+    const bool coded_run = !s->k1_only;
+    if (coded_run) { stream_note_witness(s, 0, pairs); s->wit_dirty_full = false; }
     for (uint32_t i = 0; i < pairs; i++) {
-        if (!s->last_infos[i].raw) s->last_infos[i].wlen = s->h_wlen[i];
+        s->last_infos[i].wlen = (coded_run && !s->last_infos[i].raw) ? s->h_wlen[i] : 0;
         if (infos) infos[i] = s->last_infos[i];
     }
     return RBF_OK;
 }
 
-extern "C" int rbf_stream_stage_ms(rbf_stream* s, double out[5]) {
+extern "C" int rbf_stream_stage_ms(rbf_stream* s, double out[6]) {
     if (!s || !out) return RBF_ERR_INVALID;
     rbf_ctx* c = s->c;
     if (!s->staged) return set_err(c, RBF_ERR_STATE, "no fully staged encode has run");
     CK(c, cudaEventSynchronize(s->ev[5]));
-    for (int i = 0; i < 5; i++) { float f = 0; CK(c, cudaEventElapsedTime(&f, s->ev[i], s->ev[i + 1])); out[i] = f; }
+    auto span = [&](int a, int b, double* o) -> cudaError_t { float f = 0; cudaError_t e = cudaEventElapsedTime(&f, s->ev[a], s->ev[b]); *o = f; return e; };
+    CK(c, span(0, 1, &out[0]));     // K1: first launch .. end of the last range (runs beside K2 of the earlier ranges)
+    CK(c, span(0, 3, &out[1]));     // everything in front of K3: K1 + host (k, l, T) round trips + K2, as overlapped
+    CK(c, span(2, 3, &out[2]));     // K2: first launch .. end of the last range
+    CK(c, span(3, 4, &out[3]));     // K3
+    CK(c, span(4, 5, &out[4]));     // K3b (pass count, witness, packbits order)
+    CK(c, span(0, 5, &out[5]));     // whole encode
     return RBF_OK;
 }
 
@@ -780,10 +952,33 @@ extern "C" int rbf_stream_fetch(rbf_stream* s, uint32_t pair, uint8_t* bitmap, u
     if (!s) return RBF_ERR_INVALID;
     rbf_ctx* c = s->c;
     if (pair >= s->last_pairs) return set_err(c, RBF_ERR_INVALID, "pair %u was not encoded", pair);
+    if (s->last_k1_only && (bitmap || witness))
+        return set_err(c, RBF_ERR_STATE, "the last encode stopped after K1 (k1_only): there is no bitmap / witness to fetch");
     const rbf_mask_info& in = s->last_infos[pair];
     if (bitmap && !in.raw) { size_t nb = (in.l + 7) / 8; CK(c, cudaMemcpyAsync(bitmap, s->d_bits + (size_t)pair * s->mask_stride_w, nb, cudaMemcpyDeviceToHost, c->st)); c->d2h += nb; }
     if (witness && !in.raw && in.wlen) { size_t nb = (in.wlen + 7) / 8; CK(c, cudaMemcpyAsync(witness, s->d_wit + (size_t)pair * s->mask_stride_w, nb, cudaMemcpyDeviceToHost, c->st)); c->d2h += nb; }
     if (mask_little) { size_t nb = (s->npix + 7) / 8; CK(c, cudaMemcpyAsync(mask_little, s->d_mask + (size_t)pair * s->mask_stride_w, nb, cudaMemcpyDeviceToHost, c->st)); c->d2h += nb; }
+    CK(c, cudaStreamSynchronize(c->st));
+    return RBF_OK;
+}
+
+// One strided copy per output kind for pairs [first, first+count) and ONE synchronisation (the GOP loop's batched fetch).
+extern "C" int rbf_stream_fetch_batch(rbf_stream* s, uint32_t first, uint32_t count, uint8_t* bitmaps, uint64_t bitmap_slot,
+                                      uint8_t* witness, uint64_t witness_slot, uint8_t* masks_little, uint64_t mask_slot) {
+    if (!s) return RBF_ERR_INVALID;
+    rbf_ctx* c = s->c;
+    if (count == 0 || (uint64_t)first + count > s->last_pairs) return set_err(c, RBF_ERR_INVALID, "pairs [%u,%u) were not encoded", first, first + count);
+    if (s->last_k1_only && (bitmaps || witness))
+        return set_err(c, RBF_ERR_STATE, "the last encode stopped after K1 (k1_only): there is no bitmap / witness to fetch");
+    const size_t stride = s->mask_stride_w * 4;
+    auto copy2d = [&](uint8_t* dst, uint64_t slot, const uint32_t* src) -> cudaError_t {
+        const size_t w = slot < stride ? (size_t)slot : stride;
+        c->d2h += (int64_t)w * count;
+        return cudaMemcpy2DAsync(dst, slot, (const uint8_t*)src + (size_t)first * stride, stride, w, count, cudaMemcpyDeviceToHost, c->st);
+    };
+    if (bitmaps && bitmap_slot) CK(c, copy2d(bitmaps, bitmap_slot, s->d_bits));
+    if (witness && witness_slot) CK(c, copy2d(witness, witness_slot, s->d_wit));
+    if (masks_little && mask_slot) CK(c, copy2d(masks_little, mask_slot, s->d_mask));
     CK(c, cudaStreamSynchronize(c->st));
     return RBF_OK;
 }
@@ -797,6 +992,8 @@ extern "C" int rbf_stream_encode_host(rbf_stream* s, const void* host_frames, ui
     if (nframes > s->max_frames || pairs > s->max_pairs) return set_err(c, RBF_ERR_INVALID, "stream too small for %u frames", nframes);
     CK(c, cudaSetDevice(c->device));
     if (!c->st_copy) CK(c, cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+    if (!c->st_d2h) { CK(c, cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking)); CK(c, cudaEventCreateWithFlags(&c->ev_d2h, cudaEventDisableTiming)); }
+    if (s->k1_only) return set_err(c, RBF_ERR_STATE, "rbf_stream_encode_host on a k1_only stream");
     // chunks of frames: all H2D copies are queued on the copy stream up front (pinned source), the compute stream
     // encodes a chunk's pairs as soon as its frames have landed, so PCIe transfer and kernels overlap
     const uint32_t CH = c->host_chunk_frames > 1 ? (uint32_t)c->host_chunk_frames : 32u;
@@ -824,20 +1021,27 @@ extern "C" int rbf_stream_encode_host(rbf_stream* s, const void* host_frames, ui
         CK(c, cudaStreamWaitEvent(c->st, s->ev_copy[k], 0));
         int rc = stream_encode_range(s, p0, cnt, p0 + k, pi.data(), ci.data(), threshold, sd, nullptr, nullptr, false);
         if (rc) return rc;
+        // the packed results of this chunk go back on their own stream, beside the kernels of the next chunk
+        CK(c, cudaEventRecord(c->ev_d2h, c->st));
+        CK(c, cudaStreamWaitEvent(c->st_d2h, c->ev_d2h, 0));
         if (bitmaps && bitmap_slot) {
             const size_t w = bitmap_slot < stride ? bitmap_slot : stride;
             CK(c, cudaMemcpy2DAsync(bitmaps + (size_t)p0 * bitmap_slot, bitmap_slot, (const uint8_t*)s->d_bits + (size_t)p0 * stride, stride,
-                                    w, cnt, cudaMemcpyDeviceToHost, c->st));
+                                    w, cnt, cudaMemcpyDeviceToHost, c->st_d2h));
             c->d2h += (int64_t)w * cnt;
         }
         if (witness && witness_slot) {
             const size_t w = witness_slot < stride ? witness_slot : stride;
             CK(c, cudaMemcpy2DAsync(witness + (size_t)p0 * witness_slot, witness_slot, (const uint8_t*)s->d_wit + (size_t)p0 * stride, stride,
-                                    w, cnt, cudaMemcpyDeviceToHost, c->st));
+                                    w, cnt, cudaMemcpyDeviceToHost, c->st_d2h));
             c->d2h += (int64_t)w * cnt;
         }
     }
+    CK(c, cudaEventRecord(c->ev_d2h, c->st_d2h));        // the caller's timer / next call on `st` sees the copies done
+    CK(c, cudaStreamWaitEvent(c->st, c->ev_d2h, 0));
     CK(c, cudaStreamSynchronize(c->st));
+    stream_note_witness(s, 0, pairs);
+    s->wit_dirty_full = false;
     // one contiguous prefix array for later decode_verify over all pairs
     {
         const uint32_t ncent = (uint32_t)((s->npix + 99) / 100);

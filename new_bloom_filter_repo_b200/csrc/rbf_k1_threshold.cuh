@@ -19,6 +19,12 @@ __device__ __forceinline__ int absdiff_sample(uint32_t a, uint32_t b) {
     }
 }
 
+// cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) of the reference's non-YUV colour branch (ivc:792-795): OpenCV's 15-bit
+// fixed point, identical for 8- and 16-bit samples (checked against cv2 4.13 in tests/golden/make_golden.py)
+__device__ __forceinline__ uint32_t bgr2gray_fixed(uint32_t b, uint32_t g, uint32_t r) {
+    return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15;
+}
+
 // 256-bit streaming load: one 32 B sector per thread per instruction (LDG.E.256 on sm_100a)
 __device__ __forceinline__ void ldg256_stream(const void* p, uint32_t* r) {
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -41,9 +47,10 @@ __device__ __forceinline__ void yuv8_group4(uint32_t a0, uint32_t a1, uint32_t a
     nd = min(f0, 1u) | (min(f1, 1u) << 1) | (min(f2, 1u) << 2) | (min(f3, 1u) << 3);
 }
 
-template <int PB, int S>
+template <int PB, int S, bool GRAY = false>
 __global__ void __launch_bounds__(256) k_threshold(const PairJob* __restrict__ pairs, uint32_t npix, int thr, int any_mode,
                                                    uint32_t* __restrict__ ones, uint32_t* __restrict__ resid) {
+    static_assert(!GRAY || PB == 3 * S, "BGR->gray needs three samples per pixel");
     const PairJob pj = pairs[blockIdx.y];
     const uint32_t nwords = (npix + 31u) >> 5;
     uint32_t cnt_ones = 0, cnt_res = 0;
@@ -54,7 +61,7 @@ __global__ void __launch_bounds__(256) k_threshold(const PairJob* __restrict__ p
         const uint32_t px0 = w << 5;
         uint32_t m = 0, r = 0;
         if (px0 + 32u <= npix) {
-            if (PB == 3 && S == 1) {
+            if (PB == 3 && S == 1 && !GRAY) {
                 uint32_t A[24], B[24];
                 const uint8_t* pa = pj.prev + (size_t)px0 * 3;
                 const uint8_t* pb = pj.curr + (size_t)px0 * 3;
@@ -88,8 +95,15 @@ __global__ void __launch_bounds__(256) k_threshold(const PairJob* __restrict__ p
                     for (int k = 0; k < PXH; k++) {
                         const int o = k * PB;              // byte offset of the pixel (compile-time)
                         const uint32_t smask = (S == 1) ? 0xffu : 0xffffu;
-                        const uint32_t ya = (A[o >> 2] >> (8 * (o & 3))) & smask;
-                        const uint32_t yb = (B[o >> 2] >> (8 * (o & 3))) & smask;
+                        uint32_t ya = (A[o >> 2] >> (8 * (o & 3))) & smask;
+                        uint32_t yb = (B[o >> 2] >> (8 * (o & 3))) & smask;
+                        if (GRAY) {                        // samples 1 and 2 of the pixel (compile-time offsets; S == 2 samples are 2-aligned)
+                            const int p1 = o + S, p2 = o + 2 * S;
+                            const uint32_t a1 = (A[p1 >> 2] >> (8 * (p1 & 3))) & smask, a2 = (A[p2 >> 2] >> (8 * (p2 & 3))) & smask;
+                            const uint32_t b1 = (B[p1 >> 2] >> (8 * (p1 & 3))) & smask, b2 = (B[p2 >> 2] >> (8 * (p2 & 3))) & smask;
+                            ya = bgr2gray_fixed(ya, a1, a2);
+                            yb = bgr2gray_fixed(yb, b1, b2);
+                        }
                         uint32_t anyd = 0;                 // any byte of the pixel differs
 #pragma unroll
                         for (int q = 0; q < PB; q++) {
@@ -108,6 +122,12 @@ __global__ void __launch_bounds__(256) k_threshold(const PairJob* __restrict__ p
                 const uint8_t* b = pj.curr + (size_t)(px0 + k) * PB;
                 uint32_t ya = a[0], yb = b[0];
                 if (S == 2) { ya |= (uint32_t)a[1] << 8; yb |= (uint32_t)b[1] << 8; }
+                if (GRAY) {
+                    uint32_t a1 = a[S], a2 = a[2 * S], b1 = b[S], b2 = b[2 * S];
+                    if (S == 2) { a1 |= (uint32_t)a[3] << 8; a2 |= (uint32_t)a[5] << 8; b1 |= (uint32_t)b[3] << 8; b2 |= (uint32_t)b[5] << 8; }
+                    ya = bgr2gray_fixed(ya, a1, a2);
+                    yb = bgr2gray_fixed(yb, b1, b2);
+                }
                 uint32_t anyd = 0;
                 for (int q = 0; q < PB; q++) anyd |= (uint32_t)(a[q] ^ b[q]);
                 const uint32_t bit = ((absdiff_sample<PB, S>(ya, yb) > thr) || (any_mode && anyd != 0u)) ? 1u : 0u;

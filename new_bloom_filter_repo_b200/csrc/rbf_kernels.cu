@@ -111,7 +111,7 @@ __device__ __forceinline__ void or_bits128(uint32_t* __restrict__ W, uint64_t bi
 // ------------------------------------------------------------------------------------------
 template <int PB, int S>
 static cudaError_t launch_threshold_t(const PairJob* d_pairs, int F, uint32_t npix, int thr, int any_mode, uint32_t* d_ones,
-                                      uint32_t* d_resid, int variant, int sm_count, cudaStream_t st) {
+                                      uint32_t* d_resid, int variant, int sm_count, int ctas_per_sm, cudaStream_t st) {
     const uint32_t nwords = (npix + 31u) >> 5;
     constexpr uint32_t TP = TMA_TILE_BYTES / PB;
     if (variant == 1 && npix >= TP && (TP / 32u / (TMA_THREADS / 32)) <= 32u) {
@@ -132,21 +132,40 @@ static cudaError_t launch_threshold_t(const PairJob* d_pairs, int F, uint32_t np
         return cudaGetLastError();
     }
     uint32_t bx = (nwords + 255u) / 256u;
-    const uint32_t cap = (uint32_t)(sm_count * 32);
+    const uint32_t cap = (uint32_t)(sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 32));
     if ((uint64_t)bx * (uint64_t)F > cap) { bx = (cap + (uint32_t)F - 1u) / (uint32_t)F; if (bx < 1u) bx = 1u; }
     dim3 grid(bx, (unsigned)F);
     k_threshold<PB, S><<<grid, 256, 0, st>>>(d_pairs, npix, thr, any_mode, d_ones, d_resid);
     return cudaGetLastError();
 }
 
+// gray_mode: the mask is taken on cv2.COLOR_BGR2GRAY of the three samples instead of on sample 0 (ivc:792-795)
+template <int PB, int S>
+static cudaError_t launch_threshold_gray_t(const PairJob* d_pairs, int F, uint32_t npix, int thr, int any_mode, uint32_t* d_ones,
+                                           uint32_t* d_resid, int sm_count, int ctas_per_sm, cudaStream_t st) {
+    const uint32_t nwords = (npix + 31u) >> 5;
+    uint32_t bx = (nwords + 255u) / 256u;
+    const uint32_t cap = (uint32_t)(sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 32));
+    if ((uint64_t)bx * (uint64_t)F > cap) { bx = (cap + (uint32_t)F - 1u) / (uint32_t)F; if (bx < 1u) bx = 1u; }
+    dim3 grid(bx, (unsigned)F);
+    k_threshold<PB, S, true><<<grid, 256, 0, st>>>(d_pairs, npix, thr, any_mode, d_ones, d_resid);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_threshold(const PairJob* d_pairs, int F, uint32_t npix, int channels, int sample_bytes, int thr_int,
-                             int any_mode, uint32_t* d_ones, uint32_t* d_resid, int variant, int sm_count, cudaStream_t st) {
+                             int any_mode, int gray_mode, uint32_t* d_ones, uint32_t* d_resid, int variant, int sm_count,
+                             int ctas_per_sm, cudaStream_t st) {
     if (F <= 0 || npix == 0) return cudaSuccess;
     const int pb = channels * sample_bytes;
-    if (pb == 3 && sample_bytes == 1) return launch_threshold_t<3, 1>(d_pairs, F, npix, thr_int, any_mode, d_ones, d_resid, variant, sm_count, st);
-    if (pb == 6 && sample_bytes == 2) return launch_threshold_t<6, 2>(d_pairs, F, npix, thr_int, any_mode, d_ones, d_resid, variant, sm_count, st);
-    if (pb == 1 && sample_bytes == 1) return launch_threshold_t<1, 1>(d_pairs, F, npix, thr_int, any_mode, d_ones, d_resid, variant, sm_count, st);
-    if (pb == 2 && sample_bytes == 2) return launch_threshold_t<2, 2>(d_pairs, F, npix, thr_int, any_mode, d_ones, d_resid, variant, sm_count, st);
+    if (gray_mode) {
+        if (pb == 3 && sample_bytes == 1) return launch_threshold_gray_t<3, 1>(d_pairs, F, npix, thr_int, any_mode, d_ones, d_resid, sm_count, ctas_per_sm, st);
+        if (pb == 6 && sample_bytes == 2) return launch_threshold_gray_t<6, 2>(d_pairs, F, npix, thr_int, any_mode, d_ones, d_resid, sm_count, ctas_per_sm, st);
+        return cudaErrorInvalidValue;
+    }
+    if (pb == 3 && sample_bytes == 1) return launch_threshold_t<3, 1>(d_pairs, F, npix, thr_int, any_mode, d_ones, d_resid, variant, sm_count, ctas_per_sm, st);
+    if (pb == 6 && sample_bytes == 2) return launch_threshold_t<6, 2>(d_pairs, F, npix, thr_int, any_mode, d_ones, d_resid, variant, sm_count, ctas_per_sm, st);
+    if (pb == 1 && sample_bytes == 1) return launch_threshold_t<1, 1>(d_pairs, F, npix, thr_int, any_mode, d_ones, d_resid, variant, sm_count, ctas_per_sm, st);
+    if (pb == 2 && sample_bytes == 2) return launch_threshold_t<2, 2>(d_pairs, F, npix, thr_int, any_mode, d_ones, d_resid, variant, sm_count, ctas_per_sm, st);
     return cudaErrorInvalidValue;
 }
 

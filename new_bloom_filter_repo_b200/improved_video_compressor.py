@@ -51,7 +51,11 @@ class RationalBloomFilter:
 
     @property
     def bit_array(self) -> np.ndarray:                        # ivc:59 (np.uint8[size], one byte per bit)
-        return self._dev.get_bits()
+        """A read-only snapshot of the device bits: in-place writes (`f.bit_array[i] = 1`) would be lost, so they raise;
+        assign a whole array instead (`f.bit_array = bits`, as ivc:290 does)."""
+        a = self._dev.get_bits()
+        a.setflags(write=False)
+        return a
 
     @bit_array.setter
     def bit_array(self, bits) -> None:                        # `bloom_filter.bit_array = bloom_bitmap`, ivc:290
@@ -64,17 +68,35 @@ class RationalBloomFilter:
     def _determine_activation(self, item: int) -> bool:       # ivc:83-97
         return _cabi.xxh64(str(item).encode("utf-8"), self._act_seed) < _cabi.activation_threshold(self.p_activation)
 
+    @staticmethod
+    def _split(indices):
+        """uint32 items go to the decimal-index kernels; anything else the reference would hash as str(item) -- negative or
+        >= 2**32 integers -- goes through the string kernels, so `str(item)` semantics hold for every int."""
+        arr = np.asarray(indices)
+        if arr.dtype.kind in "iu" and arr.size and (arr.dtype.kind == "u" or int(arr.min()) >= 0) and int(arr.max()) < 2 ** 32:
+            return arr.astype(np.uint32, copy=False).reshape(-1), None
+        if arr.size == 0:
+            return np.zeros(0, dtype=np.uint32), None
+        return None, [str(int(x)) if isinstance(x, (int, np.integer)) else str(x) for x in np.asarray(indices, dtype=object).reshape(-1)]
+
     def add_index(self, index: int) -> None:                  # ivc:99-114
-        self._dev.add_indices([index])
+        self.add_indices([index])
 
     def check_index(self, index: int) -> bool:                # ivc:116-138
-        return bool(self._dev.check_indices([index])[0])
+        return bool(self.check_indices([index])[0])
 
     def add_indices(self, indices) -> None:                   # batch form: one launch
-        self._dev.add_indices(indices)
+        u32, strs = self._split(indices)
+        if strs is None:
+            self._dev.add_indices(u32)
+        else:
+            self._dev.add_strings(strs)
 
     def check_indices(self, indices) -> np.ndarray:
-        return self._dev.check_indices(indices).astype(bool)
+        u32, strs = self._split(indices)
+        if strs is None:
+            return self._dev.check_indices(u32).astype(bool)
+        return self._dev.check_strings(strs).astype(bool)
 
 
 class BloomFilterCompressor:
@@ -185,36 +207,41 @@ class VideoFrameCompressor:
         noise_level = self._estimate_noise_level(frame)
         return max(self.min_diff_threshold, min(self.max_diff_threshold, noise_level * self.noise_tolerance))
 
-    def _stream_for(self, shape, dtype) -> FrameStream:
-        key = (tuple(shape), np.dtype(dtype).str)
+    def _stream_for(self, shape, dtype, k1_only: bool = False, gray: bool = False) -> FrameStream:
+        """Cached 2-frame device store per (shape, dtype, options).  Options are per-stream state of the C ABI, so several
+        compressors (or threads with their own compressor) never flip a shared switch."""
+        key = (tuple(shape), np.dtype(dtype).str, bool(k1_only), bool(gray))
         s = self._streams.get(key)
         if s is None:
             ch = shape[2] if len(shape) == 3 else 1
-            s = FrameStream(shape[0], shape[1], ch, dtype, max_frames=2, max_pairs=1)
+            s = FrameStream(shape[0], shape[1], ch, dtype, max_frames=2, max_pairs=1, k1_only=k1_only, gray_mode=gray)
             self._streams[key] = s
         return s
 
+    @staticmethod
+    def _bgr2gray(a: np.ndarray) -> np.ndarray:
+        """cv2.cvtColor(a, cv2.COLOR_BGR2GRAY) for uint8/uint16 (OpenCV's 15-bit fixed point; ivc:794-795) -- used on the host
+        only to feed the adaptive-threshold noise estimate; the mask itself is computed by K1 in gray mode."""
+        x = a.astype(np.uint32)
+        return ((x[:, :, 0] * 3735 + x[:, :, 1] * 19235 + x[:, :, 2] * 9798 + 16384) >> 15).astype(a.dtype)
+
     def _calculate_frame_diff(self, prev_frame, curr_frame, threshold: Optional[float] = None):
-        """ivc:768-847 -> (binary_diff uint8 HxW, changed_values, diff_density).  The mask is computed by K1
-        (first channel = Y, `use_direct_yuv` frames or single-channel frames)."""
+        """ivc:768-847 -> (binary_diff uint8 HxW, changed_values, diff_density).  The mask is computed by K1: on the first
+        channel (Y) for `use_direct_yuv` frames, on the BGR->gray conversion otherwise (ivc:788-795), or on the single plane."""
         pd, cd = _frame_data(prev_frame), _frame_data(curr_frame)
         is_color = pd.ndim > 2 and pd.shape[2] > 1
-        if is_color and not (self.use_direct_yuv and pd.shape[2] >= 3):
-            raise NotImplementedError("BGR->gray masks (ivc:794-795) are outside the accelerated path; pass YUV frames "
-                                      "with use_direct_yuv=True")
-        if threshold is None:                                  # ivc:804-805: adaptive threshold from the current Y / gray plane
-            threshold = self._adaptive_diff_threshold(cd[:, :, 0].copy() if is_color else cd.copy())
+        gray = is_color and not (self.use_direct_yuv and pd.shape[2] >= 3)
+        if gray and pd.shape[2] != 3:
+            raise NotImplementedError("BGR->gray masks are implemented for 3-channel frames (cv2.COLOR_BGR2GRAY, ivc:794-795)")
         if pd.dtype not in (np.uint8, np.uint16) or pd.shape != cd.shape or pd.dtype != cd.dtype:
             raise ValueError("frames must be equal-shape uint8/uint16 arrays")
-        st = self._stream_for(pd.shape, pd.dtype)
+        if threshold is None:                                  # ivc:804-805: adaptive threshold from the current Y / gray plane
+            plane = (self._bgr2gray(cd) if gray else cd[:, :, 0].copy()) if is_color else cd.copy()
+            threshold = self._adaptive_diff_threshold(plane)
+        st = self._stream_for(pd.shape, pd.dtype, k1_only=True, gray=gray)
         st.upload(np.stack([pd, cd]))
-        L = _cabi.lib()
-        _cabi.check(L.rbf_set_option(_cabi.ctx(), b"k1_only", 1), _cabi.ctx())
-        try:
-            res = st.encode([0], [1], float(threshold))[0]
-        finally:
-            _cabi.check(L.rbf_set_option(_cabi.ctx(), b"k1_only", 0), _cabi.ctx())
-        _, _, flat = st.fetch(0)
+        res = st.encode([0], [1], float(threshold))[0]
+        _, _, flat = st.fetch(0)                               # k1_only stream: the mask is the only output
         binary_diff = flat.reshape(pd.shape[0], pd.shape[1]).astype(np.uint8)
         vals = st.gather_changed(1)[0]                        # N1: ordered gather on the device (ivc:810-842)
         if is_color and self.use_direct_yuv and hasattr(curr_frame, "yuv_info"):
@@ -236,7 +263,7 @@ class VideoFrameCompressor:
             if len(vals) == len(rows) * ch:
                 data[rows, cols] = vals.reshape(-1, ch) if ch > 1 else vals
         else:
-            st = self._stream_for(data.shape, data.dtype)
+            st = self._stream_for(data.shape, data.dtype, k1_only=True)
             st.upload(np.ascontiguousarray(data)[None], first=0)
             st.apply_diff(0, 1, diff_mask, vals)               # value-count mismatch leaves the base unchanged (ivc:882)
             data[...] = st.download(1)
@@ -314,7 +341,10 @@ class VideoFrameCompressor:
         return frame
 
 
-_INTER_TAG = b"\xff\xff\xff\xffRBF1"     # cannot be a FixedVideoCompressor payload (height 0xFFFFFFFF)
+_INTER_TAG_V1 = b"\xff\xff\xff\xffRBF1"   # round-1 layout: raw-passthrough masks stored as plain np.packbits bytes
+_INTER_TAG = b"\xff\xff\xff\xffRBF2"      # current: raw-passthrough masks zlib-compressed (a static scene costs ~1 KB, not n/8 B)
+# neither can be a FixedVideoCompressor payload (height 0xFFFFFFFF).  NOTE: inter payloads exist only in this implementation --
+# the reference's decoder knows keyframes only (ivc:1124); files written with keyframe_interval=1 are interchangeable.
 
 
 class ImprovedVideoCompressor:
@@ -326,6 +356,8 @@ class ImprovedVideoCompressor:
       "lossless"  (default) mask = any byte of the pixel differs, so reconstruction is always exact;
       "reference" mask = |dY| > inter_frame_threshold exactly as _calculate_frame_diff (ivc:788-808); a frame whose
                   unflagged pixels changed (chroma-only or sub-threshold changes) falls back to a keyframe.
+    The entropy stage (zlib level 9, ivc:956 / fvc:31) stays on the CPU but runs in a thread pool (`num_threads`; zlib
+    releases the GIL), and a group of `batch_size` inter frames costs ONE encode call and ONE batched device->host copy.
     """
 
     def __init__(self, noise_tolerance: float = 10.0, keyframe_interval: int = 30, min_diff_threshold: float = 3.0,
@@ -337,6 +369,7 @@ class ImprovedVideoCompressor:
         self.max_diff_threshold = max_diff_threshold
         self.bloom_threshold_modifier = bloom_threshold_modifier
         self.batch_size = batch_size
+        self.num_threads = max(1, min(32, (os.cpu_count() or 2))) if num_threads is None else max(1, int(num_threads))
         self.use_direct_yuv = use_direct_yuv
         self.verbose = verbose
         self.compressor = FixedVideoCompressor(verbose=verbose)                    # ivc:356
@@ -345,46 +378,52 @@ class ImprovedVideoCompressor:
         _cabi.ctx()                                                                 # fail now if there is no B200
 
     # ------------------------------------------------------------------ encode
-    def _encode_inter_frames(self, datas: List[np.ndarray], inter: List[int]) -> Dict[int, Optional[bytes]]:
-        """Inter-frame payloads for frame indices `inter` (each coded against frame i-1)."""
-        out: Dict[int, Optional[bytes]] = {}
+    @staticmethod
+    def _inter_payload(shape, itemsize, ch, r, bm_row, wt_row, mask_row, values) -> bytes:
+        """Assemble one inter-frame payload (runs in a worker thread; the zlib calls release the GIL)."""
+        vz = zlib.compress(values.tobytes(), 9)
+        hdr = _INTER_TAG + struct.pack("<IIIBB", shape[0], shape[1], itemsize, ch, 1 if r.raw else 0)
+        body = struct.pack("<dIIQ", r.k, r.l, r.wlen, r.ones)
+        if r.raw:                                              # passthrough branch (ivc:215-225): the mask itself, np.packbits order
+            n = shape[0] * shape[1]
+            raw_bits = np.packbits(np.unpackbits(mask_row, bitorder="little")[:n]).tobytes()
+            rz = zlib.compress(raw_bits, 9)
+            body += struct.pack("<I", len(rz)) + rz + struct.pack("<I", 0)
+        else:
+            nb, nw = (r.l + 7) // 8, (r.wlen + 7) // 8
+            body += struct.pack("<I", nb) + bm_row[:nb].tobytes() + struct.pack("<I", nw) + wt_row[:nw].tobytes()
+        body += struct.pack("<II", len(vz), values.size) + vz
+        return hdr + body
+
+    def _encode_inter_frames(self, datas: List[np.ndarray], inter: List[int], pool) -> Dict[int, object]:
+        """Futures of the inter-frame payloads for frame indices `inter` (each coded against frame i-1); None = keyframe instead."""
+        out: Dict[int, object] = {}
         if not inter:
             return out
         shape, dtype = datas[0].shape, datas[0].dtype
         ch = shape[2] if len(shape) == 3 else 1
         group = max(2, int(self.batch_size))
-        L = _cabi.lib()
-        _cabi.check(L.rbf_set_option(_cabi.ctx(), b"mask_mode", 1 if self.inter_frame_mode == "lossless" else 0), _cabi.ctx())
+        st = FrameStream(shape[0], shape[1], ch, dtype, max_frames=2 * group, max_pairs=group,
+                         mask_mode=1 if self.inter_frame_mode == "lossless" else 0)
         try:
-            st = FrameStream(shape[0], shape[1], ch, dtype, max_frames=2 * group, max_pairs=group)
             for g0 in range(0, len(inter), group):
                 idxs = inter[g0:g0 + group]
                 need = sorted(set(idxs) | {i - 1 for i in idxs})
                 slot = {f: s for s, f in enumerate(need)}
                 st.upload(np.stack([datas[f] for f in need]))
-                thr = float(self.inter_frame_threshold)
-                res = st.encode([slot[i - 1] for i in idxs], [slot[i] for i in idxs], thr)
-                gathered = st.gather_changed(len(idxs))            # N1: changed values of every pair, one launch
+                res = st.encode([slot[i - 1] for i in idxs], [slot[i] for i in idxs], float(self.inter_frame_threshold))
+                gathered = st.gather_changed(len(idxs))            # N1: changed values of every pair, one launch, one copy
+                any_raw = any(r.raw for r in res)
+                bms, wts, masks = st.fetch_batch(0, len(idxs), want_masks=any_raw)   # one D2H per kind, one sync per group
                 for j, i in enumerate(idxs):
                     r = res[j]
                     if r.resid and self.inter_frame_mode != "lossless":
                         out[i] = None                              # not exactly representable: keyframe instead
                         continue
-                    bm, wt, mask = st.fetch(j)
-                    values = gathered[j]                           # interleaved channel values of changed pixels
-                    vz = zlib.compress(values.tobytes(), 9)
-                    hdr = _INTER_TAG + struct.pack("<IIIBB", shape[0], shape[1], dtype.itemsize, ch, 1 if r.raw else 0)
-                    body = struct.pack("<dIIQ", r.k, r.l, r.wlen, r.ones)
-                    if r.raw:
-                        raw_bits = np.packbits(mask).tobytes()
-                        body += struct.pack("<I", len(raw_bits)) + raw_bits + struct.pack("<I", 0)
-                    else:
-                        body += struct.pack("<I", len(bm)) + bm.tobytes() + struct.pack("<I", len(wt)) + wt.tobytes()
-                    body += struct.pack("<II", len(vz), values.size) + vz
-                    out[i] = hdr + body
-            st.close()
+                    out[i] = pool.submit(self._inter_payload, shape, dtype.itemsize, ch, r, bms[j], wts[j],
+                                         masks[j] if (masks is not None and r.raw) else None, gathered[j])
         finally:
-            _cabi.check(L.rbf_set_option(_cabi.ctx(), b"mask_mode", 0), _cabi.ctx())
+            st.close()
         return out
 
     def compress_video(self, frames: List[np.ndarray], output_path: str = None, input_color_space: str = "BGR") -> Dict:
@@ -402,15 +441,22 @@ class ImprovedVideoCompressor:
         uniform = all(d.shape == datas[0].shape and d.dtype == datas[0].dtype for d in datas) and \
             datas[0].dtype in (np.uint8, np.uint16) and (datas[0].ndim == 2 or datas[0].shape[2] == 3)
         inter = [i for i in range(len(frames)) if i % ki != 0] if uniform else []
-        payloads = self._encode_inter_frames(datas, inter)
+        from concurrent.futures import ThreadPoolExecutor
         compressed_frames: List[bytes] = []
         keyframes = 0
-        for i, f in enumerate(frames):
-            pl = payloads.get(i)
-            if pl is None:
-                pl = self.compressor.compress_frame(f)
-                keyframes += 1
-            compressed_frames.append(pl)
+        with ThreadPoolExecutor(self.num_threads) as pool:
+            # keyframes (zlib level 9 of whole frames, fvc:31) start in the pool first; the GPU encodes the groups meanwhile
+            key_jobs = {i: pool.submit(self.compressor.compress_frame, frames[i]) for i in range(len(frames)) if i not in set(inter)}
+            payloads = self._encode_inter_frames(datas, inter, pool)
+            for i, f in enumerate(frames):
+                fut = payloads.get(i)
+                if fut is None:
+                    kj = key_jobs.get(i)
+                    pl = kj.result() if kj is not None else self.compressor.compress_frame(f)
+                    keyframes += 1
+                else:
+                    pl = fut.result()
+                compressed_frames.append(pl)
         if output_path:                                                             # ivc:393-406
             os.makedirs(os.path.dirname(os.path.abspath(output_path)), exist_ok=True)
             with open(output_path, "wb") as fh:
@@ -437,6 +483,7 @@ class ImprovedVideoCompressor:
 
     # ------------------------------------------------------------------ decode
     def _decode_inter(self, payload: bytes, prev):
+        v1 = payload[:len(_INTER_TAG_V1)] == _INTER_TAG_V1
         pos = len(_INTER_TAG)
         h, w, isz, ch, raw = struct.unpack_from("<IIIBB", payload, pos)
         pos += struct.calcsize("<IIIBB")
@@ -450,22 +497,32 @@ class ImprovedVideoCompressor:
         dtype = np.uint8 if isz == 1 else np.uint16
         values = np.frombuffer(zlib.decompress(payload[pos:pos + vlen]), dtype=dtype)[:vcount]
         n = h * w
+        pdata = _frame_data(prev)
+        exp_shape = (h, w, ch) if ch > 1 else (h, w)
+        if pdata.shape != exp_shape or pdata.dtype != np.dtype(dtype):
+            raise ValueError(f"inter frame {exp_shape}/{np.dtype(dtype)} does not match the previous frame {pdata.shape}/{pdata.dtype}")
+        if values.size != ones * ch:
+            raise ValueError(f"corrupt inter frame: {values.size} changed values for {ones} changed pixels x {ch} channels")
         if raw:
-            mask = np.unpackbits(bbytes)[:n]
+            rbits = bbytes if v1 else np.frombuffer(zlib.decompress(bbytes.tobytes()), dtype=np.uint8)
+            mask = np.unpackbits(rbits)[:n]
         else:
             bitmap = np.unpackbits(bbytes)[:l]
             witness = np.unpackbits(wbytes)[:wlen]
             mask = BloomFilterCompressor().decompress(bitmap, witness, n, k)
-        pdata = _frame_data(prev)
         st = getattr(self, "_dec_stream", None)
         if st is None or (st.H, st.W, st.C, st.dtype) != (h, w, ch, np.dtype(dtype)):
-            st = FrameStream(h, w, ch, dtype, max_frames=2, max_pairs=1)
+            st = FrameStream(h, w, ch, dtype, max_frames=2, max_pairs=1, k1_only=True)
             self._dec_stream, self._dec_slot, self._dec_src = st, 0, None
         if self._dec_src is not prev:                             # previous frame is not the one resident on the device
             st.upload(np.ascontiguousarray(pdata)[None], first=0)
             self._dec_slot = 0
         nxt_slot = 1 - self._dec_slot
-        st.apply_diff(self._dec_slot, nxt_slot, mask, values)     # N2: scatter on the device
+        applied = st.apply_diff(self._dec_slot, nxt_slot, mask, values)     # N2: scatter on the device
+        if applied != ones:                                       # the reference would silently return the base frame (ivc:882)
+            self._dec_src = None
+            raise ValueError(f"corrupt inter frame: the decoded mask selects {int(np.count_nonzero(mask))} pixels, the payload "
+                             f"announces {ones}")
         out = st.download(nxt_slot)
         self._dec_slot = nxt_slot
         res = YUVFrame(out) if hasattr(prev, "yuv_info") else out
@@ -488,7 +545,9 @@ class ImprovedVideoCompressor:
             raise ValueError("No compressed frames provided")                       # ivc:487-488
         frames = []
         for c in compressed_frames:
-            if c[:len(_INTER_TAG)] == _INTER_TAG:
+            if c[:len(_INTER_TAG)] in (_INTER_TAG, _INTER_TAG_V1):
+                if not frames:
+                    raise ValueError("inter frame without a preceding frame")
                 frames.append(self._decode_inter(c, frames[-1]))
             else:
                 frames.append(self.compressor.decompress_frame(c))

@@ -29,7 +29,7 @@ class PairResult:
 
 class FrameStream:
     def __init__(self, height: int, width: int, channels: int = 3, dtype=np.uint8, max_frames: int = 2,
-                 max_pairs: Optional[int] = None):
+                 max_pairs: Optional[int] = None, k1_only: bool = False, mask_mode: int = 0, gray_mode: bool = False):
         dt = np.dtype(dtype)
         if dt not in (np.dtype(np.uint8), np.dtype(np.uint16)):
             raise ValueError("frames must be uint8 or uint16")
@@ -42,6 +42,15 @@ class FrameStream:
                                                   self.max_pairs, C.byref(self._h)), _cabi.ctx())
         self._infos = (MaskInfo * self.max_pairs)()
         self.pairs = 0
+        self.k1_only = bool(k1_only)
+        for key, val in (("k1_only", int(bool(k1_only))), ("mask_mode", int(mask_mode)), ("gray_mode", int(bool(gray_mode)))):
+            self.set_option(key, val)
+
+    def set_option(self, key: str, value: int) -> None:
+        """Per-stream option of the C ABI (rbf_stream_set_option): k1_only, mask_mode, gray_mode."""
+        _cabi.check(_cabi.lib().rbf_stream_set_option(self._h, key.encode(), int(value)), _cabi.ctx())
+        if key == "k1_only":
+            self.k1_only = bool(value)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -89,14 +98,34 @@ class FrameStream:
     def fetch(self, pair: int, want_mask: bool = True):
         """-> (bitmap_packbits uint8[ceil(l/8)], witness_packbits uint8[ceil(wlen/8)], mask uint8[n] or None)."""
         mi = self._infos[pair]
-        bm = np.zeros((int(mi.l) + 7) // 8, dtype=np.uint8)
-        wt = np.zeros((int(mi.wlen) + 7) // 8, dtype=np.uint8)
+        if self.k1_only:                                   # the encode stopped after K1: only the mask exists
+            bm, wt = np.zeros(0, dtype=np.uint8), np.zeros(0, dtype=np.uint8)
+        else:
+            bm = np.zeros((int(mi.l) + 7) // 8, dtype=np.uint8)
+            wt = np.zeros((int(mi.wlen) + 7) // 8, dtype=np.uint8)
         mk = np.zeros((self.npix + 7) // 8, dtype=np.uint8) if want_mask else None
         _cabi.check(_cabi.lib().rbf_stream_fetch(self._h, int(pair), _cabi.ptr(bm) if bm.size else None,
                                                  _cabi.ptr(wt) if wt.size else None,
                                                  _cabi.ptr(mk) if mk is not None else None), _cabi.ctx())
         mask = np.unpackbits(mk, bitorder="little")[: self.npix] if mk is not None else None
         return bm, wt, mask
+
+    def fetch_batch(self, first: int, count: int, want_masks: bool = False):
+        """Packed outputs of pairs [first, first+count) with one D2H copy per kind and one sync:
+        -> (bitmaps uint8[count, bslot], witnesses uint8[count, wslot], masks uint8[count, ceil(n/8)] or None);
+        pair j's bitmap is bitmaps[j, :ceil(l_j/8)] (np.packbits order), its witness witnesses[j, :ceil(wlen_j/8)]."""
+        infos = [self._infos[first + j] for j in range(count)]
+        bslot = max(16, (max((int(m.l) + 7) // 8 for m in infos) + 15) // 16 * 16)
+        wslot = max(16, (max((int(m.wlen) + 7) // 8 for m in infos) + 15) // 16 * 16)
+        bm = np.zeros((count, bslot), dtype=np.uint8)
+        wt = np.zeros((count, wslot), dtype=np.uint8)
+        mslot = (self.npix + 7) // 8
+        mk = np.zeros((count, mslot), dtype=np.uint8) if want_masks else None
+        coded = not self.k1_only
+        _cabi.check(_cabi.lib().rbf_stream_fetch_batch(self._h, int(first), int(count), _cabi.ptr(bm) if coded else None, bslot,
+                                                       _cabi.ptr(wt) if coded else None, wslot,
+                                                       _cabi.ptr(mk) if mk is not None else None, mslot), _cabi.ctx())
+        return bm, wt, mk
 
     def decode_verify(self, pairs: Optional[int] = None) -> np.ndarray:
         """Decode every encoded pair on the GPU from its own bitmap + witness (ivc:268-307) and
@@ -133,9 +162,10 @@ class FrameStream:
         return out
 
     def stage_ms(self) -> dict:
-        out = (C.c_double * 5)()
+        out = (C.c_double * 6)()
         _cabi.check(_cabi.lib().rbf_stream_stage_ms(self._h, out), _cabi.ctx())
-        return dict(zip(("k1_threshold", "host_params", "k2_insert", "k3_query", "k3b_witness"), [float(x) for x in out]))
+        return dict(zip(("k1_threshold", "front_k1_host_k2", "k2_insert", "k3_query", "k3b_witness", "encode_total"),
+                        [float(x) for x in out]))
 
     def encode_host(self, frames: np.ndarray, threshold: float, seeds=_cabi.IVC_SEEDS, bitmap_slot: int = 0,
                     witness_slot: int = 0, out_bitmaps: np.ndarray = None, out_witness: np.ndarray = None):

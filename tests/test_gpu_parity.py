@@ -223,16 +223,18 @@ def test_threshold_kernel_variants_vs_oracle(pkg, co, variant, shape, dtype, thr
     prev, curr = synth_pair(shape[0], shape[1], 99, 0.05, dtype)
     curr[0, 0, 1] ^= 1          # chroma-only change: not in the Y mask, counted as residual
     omask, oones = co.frame_diff_mask(prev, curr, thr)
-    st = pkg.FrameStream(shape[0], shape[1], 3, dtype, max_frames=2, max_pairs=1)
+    st = pkg.FrameStream(shape[0], shape[1], 3, dtype, max_frames=2, max_pairs=1, k1_only=True)
     st.upload(np.stack([prev, curr]))
     pkg._cabi.check(L.rbf_set_option(ctx, b"k1_variant", variant), ctx)
-    pkg._cabi.check(L.rbf_set_option(ctx, b"k1_only", 1), ctx)
     try:
         res = st.encode([0], [1], thr)[0]
     finally:
         L.rbf_set_option(ctx, b"k1_variant", 0)
-        L.rbf_set_option(ctx, b"k1_only", 0)
-    _, _, mask = st.fetch(0)
+    bm, wt, mask = st.fetch(0)
+    assert res.wlen == 0 and bm.size == 0 and wt.size == 0      # k1_only: no coder outputs, never garbage lengths
+    with pytest.raises(pkg.RbfError):                              # the C ABI refuses a bitmap pointer after a k1_only encode
+        buf = np.zeros(16, dtype=np.uint8)
+        pkg._cabi.check(L.rbf_stream_fetch(st._h, 0, pkg._cabi.ptr(buf), None, None), ctx)
     assert res.ones == oones
     assert np.array_equal(mask.reshape(shape), omask)
     anyd = (prev != curr).any(axis=2)

@@ -194,3 +194,59 @@ def test_string_filters():
         assert po.get_optimal_size(rec["n"], rec["p"]) == rec["size"]
     for rec in g["optimal_hash_count"]:
         assert float(po.get_optimal_hash_count(rec["m"], rec["n"])).hex() == rec["k"]
+
+
+# ---- oracle/ref_port.py: the loop-for-loop port behind `bench.py --impl reference` and `cpu_baseline`
+def test_ref_port_compress_cases():
+    from oracle import ref_port as rp
+    g = golden_json("compress_kat.json")
+    done = 0
+    for rec in g["cases"]:
+        if rec["n"] > 70000:
+            continue
+        m = mask_for(rec)
+        bitmap, wit, p, n, ratio = rp.compress(m)
+        assert float(p).hex() == rec["p"] and n == rec["n"]
+        if rec["raw"]:
+            assert len(wit) == 0 and np.array_equal(bitmap, m)
+            continue
+        k, l = rp.calculate_optimal_params(n, p)
+        assert (float(k).hex(), l) == (rec["k"], rec["l"])
+        wit = np.asarray(wit, dtype=np.uint8)
+        assert len(bitmap) == rec["bitmap_len"] and len(wit) == rec["witness_len"]
+        assert sha(np.packbits(bitmap)) == rec["bitmap_sha256"]
+        assert sha(np.packbits(wit)) == rec["witness_sha256"]
+        assert float(ratio).hex() == rec["ratio"]
+        done += 1
+    assert done >= 3
+
+
+def test_ref_port_filter_kat_and_explicit_k():
+    from oracle import ref_port as rp
+    g = golden_json("filter_kat.json")
+    for rec in g["filters"]:
+        f = rp.RationalBloomFilter(rec["size"], rec["k"])
+        assert f.floor_k == rec["floor_k"] and float(f.p_activation).hex() == rec["p_activation"]
+        for it, probes, act in zip(rec["items"], rec["probes"], rec["activation"]):
+            assert [f._get_hash_indices(it, i) for i in range(f.floor_k + 1)] == probes
+            assert f._determine_activation(it) == act
+    c = golden_json("compress_kat.json")
+    e = c["explicit_k2.3"]
+    m = mask_for(c["cases"][0])
+    f = rp.RationalBloomFilter(e["size"], e["k"])
+    for i in np.nonzero(m)[0]:
+        f.add_index(int(i))
+    wit = np.array([m[i] for i in range(len(m)) if f.check_index(i)], dtype=np.uint8)
+    assert int(f.bit_array.sum()) == e["bits_set"] and len(wit) == e["witness_len"]
+    assert sha(np.packbits(f.bit_array)) == e["bitmap_sha256"]
+    assert sha(np.packbits(wit)) == e["witness_sha256"]
+
+
+def test_ref_port_frame_diff_masks():
+    from oracle import ref_port as rp
+    g = golden_json("frames_kat.json")
+    for rec in g["cases"]:
+        prev, curr = golden_pair(rec)
+        m = rp.frame_diff_mask(prev, curr, rec["threshold"])
+        assert int(m.sum()) == rec["ones"]
+        assert sha(np.packbits(m.reshape(-1))) == rec["mask_sha256"]
