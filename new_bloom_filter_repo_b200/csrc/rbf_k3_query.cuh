@@ -183,18 +183,7 @@ __device__ __forceinline__ uint32_t probe_bit(uint32_t sm_addr, uint32_t sm_addr
     return (word >> (idx & 31u)) & 1u;
 }
 
-// fast reductions for 2 <= m <= 2^30 (the staged kernel is only launched then)
-__device__ __forceinline__ uint32_t mod_fast(uint64_t h, const FastMod& f, uint32_t neg_m) {
-    const uint32_t hh = (uint32_t)(h >> 32), hl = (uint32_t)h;
-    const uint32_t q = hh * f.Mh + __umulhi(hh, f.Ml) + __umulhi(hl, f.Mh);
-    uint32_t r = q * neg_m + hl;                                       // hl - q*m in one IMAD (neg_m = 2^32 - m from the host)
-    r = min(r, r - 2u * f.m);
-    return min(r, r - f.m);
-}
-__device__ __forceinline__ uint32_t addmod_fast(uint32_t a, uint32_t b, uint32_t m) {
-    const uint32_t s = a + b;
-    return min(s, s - m);
-}
+// mod_fast / addmod_fast (exact h mod m for 2 <= m <= 2^30) live in rbf_k2_insert.cuh
 
 // pass bit of (owner lane, x, y) into the owner's 128-bit accumulator
 __device__ __forceinline__ void deliver_pass(uint32_t pacc_addr, uint32_t tag, bool p) {
@@ -809,4 +798,236 @@ k_query2c(const FrameJob* __restrict__ jobs, const uint32_t* __restrict__ cent_p
         g = seg_end;
     }
     cluster_sync_all();                                               // a peer may still be reading this CTA's half
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 (decade tiles, round 2: `query_variant` 5, the default).  Same tiles as k_query3 with the slack taken out:
+//   * stage B only runs FULL batches of 32 records; the < 32 survivors left over at the end of a tile are moved to the front of
+//     the buffer and consumed together with the next tile's (they fetch the decade state of the tile they came from; a record
+//     is never carried over more than one tile, and the last tile of a slab drains everything).  k_query3 ran ~0.9 partial
+//     batches per decade = 7 % of all issued instructions.
+//   * the survivor scatter is 4 instructions per position (predicate from the survivor bit, record = LOP3, predicated STS,
+//     predicated address increment) instead of the 7 the compiler made of `off += p ? 4 : 0`.
+//   * TY = 5 (half-decade tiles): records {idx:24, lane:5, y:3} -- filters up to 2^24 bits (8K frames at k* = 4) stay on the
+//     tile kernel; with the carry, half tiles no longer pay for half-full batches.
+//   * one digit-constant table per CTA instead of one per warp.
+// Results are identical to every other formulation (tests/test_gpu_parity.py::test_query_kernel_variants_vs_oracle).
+// ------------------------------------------------------------------------------------------
+#ifndef RBF_Q4_WARPS
+#define RBF_Q4_WARPS 28
+#endif
+constexpr int Q4_WARPS = RBF_Q4_WARPS, Q4_THREADS = 32 * Q4_WARPS;
+constexpr int Q4_TABLE_WORDS = 32;                                     // 10 x uint64 digit constants, padded
+template <int TY> struct Q4Cfg {
+    static constexpr int BUF = 32 * TY + 32;                            // a tile's survivors (worst case) + carried records (< 32)
+    static constexpr int YB = (TY == 10) ? 4 : 3;                       // bits of y inside the tile
+    static constexpr int IDXB = 27 - YB;                                // 23 or 24 bits of probe index
+    static constexpr int WARP_WORDS = BUF + (Q2_RING * 8 + 32 * 16) / 4;   // tile buffer, C ring, pass accumulators
+};
+
+// survivor record scatter: `if (bit) { *off = rec; off += 4; }` as two predicated instructions
+__device__ __forceinline__ void scatter_if(uint32_t& off, uint32_t rec, uint32_t bit) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.shared.u32 [%0], %1;\n @q add.u32 %0, %0, 4;\n}" : "+r"(off) : "r"(rec), "r"(bit) : "memory");
+}
+
+template <int KIND, int FKT, int PM, int TY>
+__device__ __noinline__ void query_slab_tiled2(const FilterK K, uint32_t sm_addr, const uint32_t* __restrict__ gl, uint32_t sm_words,
+                                               const uint32_t* __restrict__ mask, uint32_t n, uint32_t slab_c0, uint32_t c_end,
+                                               uint4* __restrict__ pass4, uint32_t buf_addr, uint32_t rb_addr) {
+    using Cfg = Q4Cfg<TY>;
+    constexpr uint32_t IDXM = (1u << Cfg::IDXB) - 1u;
+    const uint32_t qc_addr = buf_addr + 4u * Cfg::BUF, pacc_addr = qc_addr + 8u * Q2_RING;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t c = slab_c0 + lane;
+    const bool active = c < c_end;
+    const Century cen = make_century(active ? c : slab_c0);
+    const uint64_t C1 = century_state(cen, K.s1), C2 = century_state(cen, K.s2), CA = century_state(cen, K.sA);
+    const uint32_t nvalid = active ? min(100u, n - 100u * c) : 0u;
+    uint64_t skip_lo = 0, skip_hi = 0;                               // known members and positions beyond n need no hashing
+    if (active && mask != nullptr) { const Bits128 mb = load_bits100(mask, c, nvalid); skip_lo = mb.lo; skip_hi = mb.hi; }
+    if (nvalid < 64u) { skip_hi = ~0ull; skip_lo |= ~((1ull << nvalid) - 1ull); }
+    else skip_hi |= ~((1ull << (nvalid - 64u)) - 1ull);
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t ltag = lane << Cfg::IDXB;
+    uint32_t qc_head = 0, qc_cnt = 0;
+    uint32_t rem = 0, xp = 0, yoffp = 0;                             // carried records: count, decade and y offset of their tile
+    uint64_t D2p = 0;                                                // ... and that tile's (prepared) decade state of seed 2
+#pragma unroll 1
+    for (uint32_t x = 0; x < 10u; x++) {
+        const uint64_t D1 = decade_prep<KIND>(decade_state_t<KIND>(C1, K.s1, x));
+        const uint64_t D2 = decade_prep<KIND>(decade_state_t<KIND>(C2, K.s2, x));
+        const uint32_t p0 = 10u * x;
+        const uint64_t sh = (p0 < 64u) ? ((skip_lo >> p0) | (p0 ? (skip_hi << (64u - p0)) : 0ull)) : (skip_hi >> (p0 - 64u));
+#pragma unroll
+        for (int h = 0; h < 10 / TY; h++) {
+            // ---- stage A: TY positions per lane, y compile-time, independent hash chains
+            uint32_t idx0[TY];
+            uint32_t sv = 0;
+#pragma unroll
+            for (int yy = 0; yy < TY; yy++) {
+                const uint32_t y = (uint32_t)(h * TY + yy);
+                idx0[yy] = mod_fast(finish_prep<KIND>(D1, K.s1, y, rot_digit_const(y)), K.fm, K.nm);
+                sv |= probe_bit<PM>(sm_addr, 0u, gl, sm_words, idx0[yy]) << yy;
+            }
+            sv &= ~(uint32_t)(sh >> (h * TY)) & ((1u << TY) - 1u);
+            // ---- one scan per tile places the survivors behind the carried records
+            const uint32_t cnt = __popc(sv);
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= (uint32_t)d) inc += t;
+            }
+            const uint32_t tot2 = rem + __shfl_sync(0xffffffffu, inc, 31);
+            uint32_t off = buf_addr + 4u * (rem + inc - cnt);
+#pragma unroll
+            for (int yy = 0; yy < TY; yy++)
+                scatter_if(off, idx0[yy] | ltag | ((uint32_t)yy << (Cfg::IDXB + 5)), sv & (1u << yy));
+            __syncwarp();
+            // ---- stage B: full batches only (the last tile of the slab drains the rest)
+            const bool last_tile = (x == 9u) && (h == 10 / TY - 1);
+            uint32_t nproc = last_tile ? tot2 : (tot2 & ~31u);
+            if (nproc == 0u && rem != 0u) nproc = tot2;              // a record is carried over one tile at most
+            const uint32_t yoff = (uint32_t)(h * TY);
+#pragma unroll 1
+            for (uint32_t b = 0; b < nproc; b += 32u) {
+                const uint32_t g = b + lane;
+                const bool have = g < nproc;
+                const uint32_t rec = lds32(buf_addr + 4u * min(g, (uint32_t)(Cfg::BUF - 1)));
+                const uint32_t owner = (rec >> Cfg::IDXB) & 31u;
+                uint32_t y = (rec >> (Cfg::IDXB + 5)) + yoff, xr = x;
+                uint64_t D2o = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)D2, owner) |
+                               ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(D2 >> 32), owner) << 32);
+                if (b == 0u && rem != 0u) {                          // warp-uniform: the batch that holds the carried records
+                    const uint64_t D2q = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)D2p, owner) |
+                                         ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(D2p >> 32), owner) << 32);
+                    if (g < rem) { D2o = D2q; y = (rec >> (Cfg::IDXB + 5)) + yoffp; xr = xp; }
+                }
+                if (!have) y = 0u;
+                uint64_t rb = 0;
+                if (kind_ends_in_byte<KIND>()) { const uint2 t = lds64(rb_addr + 8u * y); rb = (uint64_t)t.x | ((uint64_t)t.y << 32); }
+                const uint32_t stepm = have ? mod_fast(finish_prep<KIND>(D2o, K.s2, y, rb), K.fm, K.nm) : 0u;
+                uint32_t idx = have ? (rec & IDXM) : 0u;
+                uint32_t ok = have ? 1u : 0u;
+                if (FKT > 0) {
+#pragma unroll
+                    for (int i = 1; i < FKT; i++) {
+                        idx = addmod_fast(idx, stepm, K.fm.m);
+                        ok &= probe_bit<PM>(sm_addr, 0u, gl, sm_words, idx);
+                    }
+                } else {
+                    for (uint32_t i = 1; i < K.fk; i++) {
+                        idx = addmod_fast(idx, stepm, K.fm.m);
+                        ok &= probe_bit<PM>(sm_addr, 0u, gl, sm_words, idx);
+                    }
+                }
+                const uint32_t tag = (owner << 8) | (xr << 4) | y;
+                if (K.has_act) {
+                    idx = addmod_fast(idx, stepm, K.fm.m);           // index of probe floor_k
+                    const uint32_t b2 = __ballot_sync(0xffffffffu, ok != 0u);
+                    sts64_if(qc_addr + 8u * ((qc_head + qc_cnt + __popc(b2 & lt)) & (Q2_RING - 1)), idx, tag, ok != 0u);
+                    qc_cnt += __popc(b2);
+                    if (qc_cnt >= 32u) drain_c_ring<KIND, PM>(K, sm_addr, 0u, gl, sm_words, qc_addr, pacc_addr, lane, CA, qc_head, qc_cnt);
+                } else {
+                    deliver_pass(pacc_addr, tag, ok != 0u);
+                }
+            }
+            // ---- carry the leftover (< 32 records) to the front of the buffer
+            const uint32_t nrem = tot2 - nproc;
+            if (nrem != 0u) {
+                const uint32_t t = lds32(buf_addr + 4u * min(nproc + lane, (uint32_t)(Cfg::BUF - 1)));
+                __syncwarp();
+                sts32_if(buf_addr + 4u * lane, t, lane < nrem);
+            }
+            __syncwarp();                                            // the tile buffer is rewritten next
+            rem = nrem; xp = x; yoffp = yoff; D2p = D2;
+        }
+    }
+#pragma unroll 1
+    while (qc_cnt) drain_c_ring<KIND, PM>(K, sm_addr, 0u, gl, sm_words, qc_addr, pacc_addr, lane, CA, qc_head, qc_cnt);
+    __syncwarp();
+    uint4 acc = lds128(pacc_addr + 16u * lane);
+    sts128_if(pacc_addr + 16u * lane, 0u, 0u, 0u, 0u, true);
+    if (active) {
+        if (mask != nullptr) {                                       // known members pass (no false negatives)
+            const Bits128 mb = load_bits100(mask, c, nvalid);
+            acc.x |= (uint32_t)mb.lo; acc.y |= (uint32_t)(mb.lo >> 32); acc.z |= (uint32_t)mb.hi; acc.w |= (uint32_t)(mb.hi >> 32);
+        }
+        pass4[c] = acc;
+    }
+    __syncwarp();
+}
+
+template <int PM, int TY>
+__global__ void __launch_bounds__(Q4_THREADS, 1) k_query4(const FrameJob* __restrict__ jobs, const uint32_t* __restrict__ cent_prefix,
+                                                          int F, uint32_t smem_words_cap) {
+    using Cfg = Q4Cfg<TY>;
+    extern __shared__ __align__(128) uint32_t dyn[];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31u;   // warp-uniform for the compiler
+    const uint32_t rb_addr = smem_u32(dyn);                                    // digit constants, one table per CTA
+    const uint32_t buf = smem_u32(dyn + Q4_TABLE_WORDS + warp * Cfg::WARP_WORDS);
+    const uint32_t pacc = buf + 4u * Cfg::BUF + 8u * Q2_RING;
+    uint32_t* sbits = dyn + Q4_TABLE_WORDS + Q4_WARPS * Cfg::WARP_WORDS;
+    const uint32_t sb_addr = smem_u32(sbits);
+    sts128_if(pacc + 16u * lane, 0u, 0u, 0u, 0u, true);
+    if (threadIdx.x < 16u) {
+        const uint64_t v = threadIdx.x < 10u ? c_rot_digit[threadIdx.x] : 0ull;
+        sts64_if(rb_addr + 8u * threadIdx.x, (uint32_t)v, (uint32_t)(v >> 32), true);
+    }
+    const uint32_t total = cent_prefix[F];
+    const uint32_t lo = (uint32_t)(((uint64_t)total * blockIdx.x) / gridDim.x);
+    const uint32_t hi = (uint32_t)(((uint64_t)total * (blockIdx.x + 1)) / gridDim.x);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (lo >= hi) return;
+    int f = 0;
+    { int a = 0, b = F; while (a < b) { int m = (a + b) >> 1; if (cent_prefix[m + 1] > lo) b = m; else a = m + 1; } f = a; }
+    uint32_t parity = 0, g = lo;
+    while (g < hi) {
+        while (cent_prefix[f + 1] <= g) f++;
+        const FrameJob& J = jobs[f];
+        const uint32_t seg_end = min(hi, cent_prefix[f + 1]);
+        const uint32_t c_begin = g - cent_prefix[f], c_end = seg_end - cent_prefix[f];
+        const uint32_t nwords = (J.l + 31u) >> 5;
+        const uint32_t sw = min((nwords + 3u) & ~3u, smem_words_cap);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&bar, sw * 4u);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(J.bits);
+            uint8_t* dst = reinterpret_cast<uint8_t*>(sbits);
+            for (uint32_t off = 0; off < sw * 4u; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, sw * 4u - off), &bar);
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+        const FilterK K = filter_consts(J);
+        uint4* pass4 = reinterpret_cast<uint4*>(J.pass);
+        for (uint32_t slab = c_begin + 32u * warp; slab < c_end; slab += 32u * Q4_WARPS) {
+            const uint32_t last = min(slab + 31u, c_end - 1u);
+            const bool uniform = slab >= 1u && ndigits_u32(slab) == ndigits_u32(last) && K.fk >= 1u && K.fm.fast && K.fm.m <= (1u << Cfg::IDXB);
+            if (uniform) {
+#define RBF_TILED2(KD)                                                                                                              \
+    if (K.fk == 3u) query_slab_tiled2<KD, 3, PM, TY>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, buf, rb_addr);          \
+    else if (K.fk == 2u) query_slab_tiled2<KD, 2, PM, TY>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, buf, rb_addr);     \
+    else query_slab_tiled2<KD, 0, PM, TY>(K, sb_addr, J.bits, sw, J.mask, J.n, slab, c_end, pass4, buf, rb_addr);
+                switch (make_century(slab).kind) {
+                case K_4B: { RBF_TILED2(K_4B) } break;
+                case K_8B: { RBF_TILED2(K_8B) } break;
+                case K_44: { RBF_TILED2(K_44) } break;
+                case K_88: { RBF_TILED2(K_88) } break;
+                default:   { RBF_TILED2(K_BB) } break;
+                }
+#undef RBF_TILED2
+            } else {                                    // century 0, a digit-count boundary, floor_k == 0 or a huge filter
+                const uint32_t c = slab + lane;
+                if (c < c_end) {
+                    BitView bv; bv.sm = sbits; bv.gl = J.bits; bv.sm_words = sw;
+                    const Bits128 r = query_century(bv, K, c, min(100u, J.n - 100u * c));
+                    pass4[c] = make_uint4((uint32_t)r.lo, (uint32_t)(r.lo >> 32), (uint32_t)r.hi, (uint32_t)(r.hi >> 32));
+                }
+            }
+        }
+        g = seg_end;
+    }
 }

@@ -171,6 +171,28 @@ cudaError_t launch_threshold(const PairJob* d_pairs, int F, uint32_t npix, int c
 
 cudaError_t launch_insert(const FrameJob* d_jobs, int F, uint32_t max_centuries, int variant, int sm_count, cudaStream_t st) {
     if (F <= 0 || max_centuries == 0) return cudaSuccess;
+    if (variant == 2) {                                   // bit array privatised in shared memory, word-wide merge
+        const int smem = query_max_smem_bytes();
+        cudaError_t e = cudaFuncSetAttribute(k_insert3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        // tasks per frame: the smallest split that fills the persistent grid evenly (<= 6 % idle in the last wave) without
+        // making tasks smaller than ~32 slabs per warp-round
+        const uint32_t nslab = (max_centuries + 31u) / 32u;
+        uint32_t S = 1, best = 1;
+        double best_waste = 1e9;
+        for (S = 1; S <= 16u; S++) {
+            if (S > 1u && nslab / S < (uint32_t)(4 * I3_WARPS)) break;
+            const uint64_t tasks = (uint64_t)F * S;
+            const uint64_t waves = (tasks + (uint64_t)sm_count - 1) / (uint64_t)sm_count;
+            const double waste = (double)(waves * (uint64_t)sm_count) / (double)tasks - 1.0 + 0.008 * S;  // each split re-clears and re-merges the copy
+            if (waste < best_waste) { best_waste = waste; best = S; }
+        }
+        S = best;
+        uint32_t grid = (uint32_t)sm_count;
+        if ((uint64_t)F * S < grid) grid = (uint32_t)((uint64_t)F * S);
+        k_insert3<<<grid, I3_THREADS, smem, st>>>(d_jobs, F, S, (uint32_t)((smem - I3_WARPS * I3_CAP * 2) / 4) & ~3u);
+        return cudaGetLastError();
+    }
     if (variant == 1) {                                   // dense, warp-compacted insert
         const uint32_t nslab = (max_centuries + 31u) / 32u;
         uint32_t bx = (nslab + I2_WARPS - 1) / I2_WARPS;
@@ -211,6 +233,30 @@ cudaError_t launch_query(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, 
     int cap = smem_bytes_cap & ~15;
     if (cap > query_max_smem_bytes()) cap = query_max_smem_bytes() & ~15;
     const uint32_t need_words = (((max_l_bits + 31u) >> 5) + 3u) & ~3u;
+    if (variant >= 5 && max_l_bits <= (1u << 24)) {       // decade tiles, round 2 (full stage-B batches with carry)
+        const bool half = (variant == 6) || max_l_bits > (1u << 23);      // half-decade tiles: 24-bit record indices
+        const int qbytes = 4 * (Q4_TABLE_WORDS + Q4_WARPS * (half ? Q4Cfg<5>::WARP_WORDS : Q4Cfg<10>::WARP_WORDS));
+        if (cap < qbytes + 1024) cap = qbytes + 1024;
+        const int bits_cap = cap - qbytes;
+        const bool fits = (size_t)need_words * 4 <= (size_t)bits_cap;
+        const int smem = qbytes + (fits ? (int)(need_words * 4 < 16 ? 16 : need_words * 4) : bits_cap);
+        uint32_t grid = (uint32_t)sm_count;
+        const uint32_t max_useful = (total_centuries + Q4_THREADS - 1) / Q4_THREADS;
+        if (grid > max_useful) grid = max_useful;
+        if (grid < 1u) grid = 1u;
+        const uint32_t words_cap = (uint32_t)((smem - qbytes) / 4);
+#define RBF_LAUNCH_Q4(PM, TY)                                                                                         \
+    do {                                                                                                              \
+        cudaError_t e = cudaFuncSetAttribute(k_query4<PM, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);    \
+        if (e != cudaSuccess) return e;                                                                               \
+        k_query4<PM, TY><<<grid, Q4_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F, words_cap);                        \
+    } while (0)
+        if (fits) { if (half) RBF_LAUNCH_Q4(0, 5); else RBF_LAUNCH_Q4(0, 10); }
+        else      { if (half) RBF_LAUNCH_Q4(1, 5); else RBF_LAUNCH_Q4(1, 10); }
+#undef RBF_LAUNCH_Q4
+        return cudaGetLastError();
+    }
+    if (variant >= 5) variant = 1;                        // m > 2^24: ring kernel
     if (variant == 4 && max_l_bits <= (1u << 23)) {       // decade tiles (records carry 23-bit indices)
         const int qbytes = Q3_WARPS * Q3_WARP_WORDS * 4;
         if (cap < qbytes + 1024) cap = qbytes + 1024;

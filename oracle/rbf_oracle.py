@@ -280,13 +280,22 @@ def decompress(bloom_bitmap: np.ndarray, witness: Sequence[int], n: int, k: floa
 # ----------------------------------------------------------------------------
 # Frame-difference mask -- VideoFrameCompressor._calculate_frame_diff, ivc:784-808
 # ----------------------------------------------------------------------------
-def frame_diff_mask(prev: np.ndarray, curr: np.ndarray, threshold: float) -> np.ndarray:
-    """Y-plane |int16(prev) - int16(curr)| > threshold  -> uint8 H x W  (ivc:788-808).
+def bgr2gray(a: np.ndarray) -> np.ndarray:
+    """cv2.cvtColor(a, cv2.COLOR_BGR2GRAY) for uint8 / uint16 (ivc:794-795).  OpenCV is a third-party dependency of the
+    reference (requirements.txt, opencv-python; 4.13.0 here): its 8/16-bit path is the 15-bit fixed point
+    (3735*B + 19235*G + 9798*R + 16384) >> 15, pinned by tests/golden/gray_kat.json (generated with the real cv2)."""
+    x = a.astype(np.uint32)
+    return ((x[:, :, 0] * 3735 + x[:, :, 1] * 19235 + x[:, :, 2] * 9798 + 16384) >> 15).astype(a.dtype)
 
-    Direct-YUV branch only (use_direct_yuv=True, channel 0 is Y); int16 wrap-around
+
+def frame_diff_mask(prev: np.ndarray, curr: np.ndarray, threshold: float, gray: bool = False) -> np.ndarray:
+    """|int16(prev) - int16(curr)| > threshold  -> uint8 H x W  (ivc:788-808) on the Y plane (use_direct_yuv=True, channel 0
+    is Y) or, gray=True, on the BGR->gray conversion of the non-YUV colour branch (ivc:792-795); int16 wrap-around
     for 16-bit samples is numpy's and is part of the reference behaviour (ivc:801).
     """
-    if prev.ndim > 2 and prev.shape[2] > 1:
+    if gray:
+        pg, cg = bgr2gray(prev), bgr2gray(curr)           # ivc:794-795
+    elif prev.ndim > 2 and prev.shape[2] > 1:
         pg = prev[:, :, 0].copy()                         # ivc:790
         cg = curr[:, :, 0].copy()                         # ivc:791
     else:

@@ -363,7 +363,51 @@ def gen_adaptive():
     dump("adaptive_kat.json", {"cases": recs})
 
 
+def gen_gray():
+    """The reference's non-YUV colour branch: cv2.COLOR_BGR2GRAY before the diff (ivc:792-795), fixed and adaptive thresholds."""
+    import cv2
+    recs = []
+    for name, h, w, seed, pc, dt, thr in [("bgr_u8_thr3", 48, 80, 71, 0.10, np.uint8, 3.0), ("bgr_u8_thr0", 37, 53, 72, 0.10, np.uint8, 0.0),
+                                           ("bgr_u8_thr20", 64, 96, 73, 0.30, np.uint8, 20.5), ("bgr_u16_thr3", 40, 72, 74, 0.05, np.uint16, 3.0),
+                                           ("bgr_u16_thr9000", 40, 72, 75, 0.20, np.uint16, 9000.0), ("bgr_u8_360p", 360, 640, 76, 0.05, np.uint8, 3.0),
+                                           ("bgr_u8_adaptive", 72, 96, 77, 0.05, np.uint8, None), ("bgr_u16_adaptive", 40, 56, 78, 0.05, np.uint16, None)]:
+        prev, curr = synth_pair(h, w, seed, pc, dt)
+        if thr is None:                                   # smooth content so that the adaptive threshold is not clamped
+            rng = np.random.default_rng(seed)
+            hi = 256 if dt == np.uint8 else 65536
+            yy, xx = np.mgrid[0:h, 0:w]
+            base = ((yy + xx) // 4 + 20).astype(np.int64) * (1 if dt == np.uint8 else 200)
+            prev = np.stack([base + rng.integers(0, 3, (h, w)) for _ in range(3)], axis=-1).astype(dt)
+            curr = prev.copy()
+            ch = rng.random((h, w)) < pc
+            curr[ch] = (curr[ch].astype(np.int64) + hi // 4) % hi
+        # single-channel changes that move the gray value by exactly the rounding boundary
+        curr[0, 0] = prev[0, 0]; curr[0, 0, 0] = (int(prev[0, 0, 0]) + 9) % (256 if dt == np.uint8 else 65536)
+        vfc = refshim.make_vfc(ivc, use_direct_yuv=False)
+        mask, changed, dens = vfc._calculate_frame_diff(prev, curr, threshold=thr)
+        g = cv2.cvtColor(curr, cv2.COLOR_BGR2GRAY)
+        rec = {"name": name, "h": h, "w": w, "seed": seed, "p_change": pc, "dtype": np.dtype(dt).name, "threshold": thr,
+               "ones": int(mask.sum()), "density": float(dens).hex(), "mask_sha256": sha(np.packbits(mask.reshape(-1))),
+               "changed_len": int(len(changed)), "changed_dtype": changed.dtype.name, "changed_sha256": sha(changed),
+               "gray_curr_sha256": sha(g)}
+        if thr is None:
+            rec["adaptive_threshold"] = float(vfc._adaptive_diff_threshold(g)).hex()
+        recs.append(rec)
+        print(name, rec["ones"], rec["changed_len"])
+    # exhaustive corner sweep of the fixed-point conversion: every (b, g, r) with two channels on a coarse grid
+    grid = np.array(sorted(set(list(range(0, 256, 5)) + [1, 2, 254, 255])), dtype=np.uint8)
+    bb, gg, rr = np.meshgrid(grid, grid, grid, indexing="ij")
+    cube = np.stack([bb, gg, rr], axis=-1).reshape(1, -1, 3)
+    cube16 = (cube.astype(np.uint16) * 257)
+    dump("gray_kat.json", {"cases": recs, "cube_u8_sha256": sha(cv2.cvtColor(cube, cv2.COLOR_BGR2GRAY)),
+                           "cube_u16_sha256": sha(cv2.cvtColor(cube16, cv2.COLOR_BGR2GRAY)), "cv2_version": cv2.__version__})
+
+
 if __name__ == "__main__":
+    if "--gray-only" in sys.argv:
+        gen_gray()
+        sys.exit(0)
+    gen_gray()
     gen_xxh64()
     gen_filter()
     gen_threshold()

@@ -7,7 +7,7 @@ import pytest
 
 from oracle import c_oracle as co
 from oracle import rbf_oracle as po
-from tests.util import golden_json, golden_npz, golden_pair, mask_for, sha
+from tests.util import golden_json, golden_npz, golden_pair, gray_cube, gray_pair, mask_for, sha
 
 
 def test_xxh64_decimal_and_strings():
@@ -250,3 +250,21 @@ def test_ref_port_frame_diff_masks():
         m = rp.frame_diff_mask(prev, curr, rec["threshold"])
         assert int(m.sum()) == rec["ones"]
         assert sha(np.packbits(m.reshape(-1))) == rec["mask_sha256"]
+
+
+def test_gray_masks_and_cv2_fixed_point():
+    """BGR->gray branch (ivc:792-795): the oracle's fixed-point restatement of cv2.COLOR_BGR2GRAY against real-cv2 fixtures."""
+    g = golden_json("gray_kat.json")
+    cube = gray_cube()
+    assert sha(po.bgr2gray(cube)) == g["cube_u8_sha256"]
+    assert sha(po.bgr2gray(cube.astype(np.uint16) * 257)) == g["cube_u16_sha256"]
+    for rec in g["cases"]:
+        prev, curr = gray_pair(rec)
+        assert sha(po.bgr2gray(curr)) == rec["gray_curr_sha256"]
+        if rec["threshold"] is None:
+            continue                                       # adaptive cases need the 5x5 median (GPU test)
+        m = po.frame_diff_mask(prev, curr, rec["threshold"], gray=True)
+        assert int(m.sum()) == rec["ones"] and sha(np.packbits(m.reshape(-1))) == rec["mask_sha256"]
+        rows, cols = np.where(m == 1)
+        ch = curr[rows, cols, :].reshape(-1)
+        assert ch.dtype.name == rec["changed_dtype"] and len(ch) == rec["changed_len"] and sha(ch) == rec["changed_sha256"]

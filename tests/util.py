@@ -50,6 +50,31 @@ def golden_pair(rec):
     return prev, curr
 
 
+def gray_pair(rec):
+    """Input pair of a tests/golden/gray_kat.json case (same construction as make_golden.gen_gray)."""
+    dt = np.dtype(rec["dtype"]).type
+    h, w, seed, pc = rec["h"], rec["w"], rec["seed"], rec["p_change"]
+    hi = 256 if dt == np.uint8 else 65536
+    prev, curr = synth_pair(h, w, seed, pc, dt)
+    if rec["threshold"] is None:
+        rng = np.random.default_rng(seed)
+        yy, xx = np.mgrid[0:h, 0:w]
+        base = ((yy + xx) // 4 + 20).astype(np.int64) * (1 if dt == np.uint8 else 200)
+        prev = np.stack([base + rng.integers(0, 3, (h, w)) for _ in range(3)], axis=-1).astype(dt)
+        curr = prev.copy()
+        ch = rng.random((h, w)) < pc
+        curr[ch] = (curr[ch].astype(np.int64) + hi // 4) % hi
+    curr[0, 0] = prev[0, 0]
+    curr[0, 0, 0] = (int(prev[0, 0, 0]) + 9) % hi
+    return prev, curr
+
+
+def gray_cube():
+    grid = np.array(sorted(set(list(range(0, 256, 5)) + [1, 2, 254, 255])), dtype=np.uint8)
+    bb, gg, rr = np.meshgrid(grid, grid, grid, indexing="ij")
+    return np.stack([bb, gg, rr], axis=-1).reshape(1, -1, 3)
+
+
 def synth_stream(h, w, frames, seed, p_seq, dtype=np.uint8):
     """SURVEY.md 8(d) generator: frame0 = gradient + small noise; frame_t = frame_{t-1} with
     Bernoulli(p_t) pixels having all channels += 64 (mod range).  Returns uint array [frames,h,w,3]."""
