@@ -811,7 +811,7 @@ k_query2c(const FrameJob* __restrict__ jobs, const uint32_t* __restrict__ cent_p
 //   * TY = 5 (half-decade tiles): records {idx:24, lane:5, y:3} -- filters up to 2^24 bits (8K frames at k* = 4) stay on the
 //     tile kernel; with the carry, half tiles no longer pay for half-full batches.
 //   * one digit-constant table per CTA instead of one per warp.
-// Results are identical to every other formulation (tests/test_gpu_parity.py::test_query_kernel_variants_vs_oracle).
+// Results are identical to every other formulation (the variant matrix in tests/test_gpu_parity.py).
 // ------------------------------------------------------------------------------------------
 #ifndef RBF_Q4_WARPS
 #define RBF_Q4_WARPS 28
