@@ -1111,9 +1111,11 @@ extern "C" int rbf_stream_gather_changed(rbf_stream* s, uint32_t pairs, uint8_t*
     offsets_out[pairs] = total;
     if (!values_out) return RBF_OK;                      // size query
     if (capacity < total) return set_err(c, RBF_ERR_INVALID, "values buffer too small: %llu < %llu", (unsigned long long)capacity, (unsigned long long)total);
-    void *d_vals, *d_jobs;
+    void *d_vals, *d_jobs, *d_gcnt;
     int rc;
-    if ((rc = scratch_get(c, 8, (size_t)total + 256, &d_vals)) || (rc = scratch_get(c, 9, sizeof(GatherJob) * pairs, &d_jobs))) return rc;
+    if ((rc = scratch_get(c, 8, (size_t)total + 256, &d_vals)) || (rc = scratch_get(c, 9, sizeof(GatherJob) * pairs, &d_jobs)) ||
+        (rc = scratch_get(c, 13, 4 * (size_t)pairs * gather_chunks((uint32_t)s->npix) + 64, &d_gcnt)))
+        return rc;
     std::vector<GatherJob> jobs(pairs);
     for (uint32_t i = 0; i < pairs; i++) {
         jobs[i].mask = s->d_mask + (size_t)i * s->mask_stride_w;
@@ -1124,7 +1126,8 @@ extern "C" int rbf_stream_gather_changed(rbf_stream* s, uint32_t pairs, uint8_t*
         jobs[i].pix_bytes = (uint32_t)pb;
     }
     CK(c, cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(GatherJob) * pairs, cudaMemcpyHostToDevice, c->st));
-    LAUNCH(c, launch_gather_scatter((const GatherJob*)d_jobs, (int)pairs, 0, nullptr, c->st));
+    LAUNCH(c, launch_gather_scatter((const GatherJob*)d_jobs, (int)pairs, 0, (uint32_t)s->npix, (uint32_t)pb, (uint32_t*)d_gcnt, nullptr, c->st));
+    c->launches++;
     if (total) { CK(c, cudaMemcpyAsync(values_out, d_vals, (size_t)total, cudaMemcpyDeviceToHost, c->st)); c->d2h += (int64_t)total; }
     CK(c, cudaStreamSynchronize(c->st));
     return RBF_OK;
@@ -1138,10 +1141,10 @@ extern "C" int rbf_stream_apply_diff(rbf_stream* s, uint32_t base_frame, uint32_
     CK(c, cudaSetDevice(c->device));
     const uint64_t pb = (uint64_t)s->C * s->S;
     const size_t mbytes = (size_t)((s->npix + 7) / 8), mwords = s->mask_stride_w;
-    void *d_mask, *d_vals, *d_job;
+    void *d_mask, *d_vals, *d_job, *d_gcnt;
     int rc;
     if ((rc = scratch_get(c, 10, mwords * 4, &d_mask)) || (rc = scratch_get(c, 8, (size_t)values_bytes + 256, &d_vals)) ||
-        (rc = scratch_get(c, 9, sizeof(GatherJob) + 64, &d_job)))
+        (rc = scratch_get(c, 9, sizeof(GatherJob) + 64, &d_job)) || (rc = scratch_get(c, 13, 4 * (size_t)gather_chunks((uint32_t)s->npix) + 64, &d_gcnt)))
         return rc;
     CK(c, cudaMemsetAsync(d_mask, 0, mwords * 4, c->st));
     CK(c, cudaMemcpyAsync(d_mask, mask_packed_little, mbytes, cudaMemcpyHostToDevice, c->st)); c->h2d += (int64_t)mbytes;
@@ -1162,7 +1165,8 @@ extern "C" int rbf_stream_apply_diff(rbf_stream* s, uint32_t base_frame, uint32_
     if (applied_pixels) *applied_pixels = 0;
     if ((uint64_t)h_cnt * pb != values_bytes) return RBF_OK;       // ivc:882: mismatch -> the base frame is returned unchanged
     CK(c, cudaMemcpyAsync(d_job, &J, sizeof J, cudaMemcpyHostToDevice, c->st));
-    LAUNCH(c, launch_gather_scatter((const GatherJob*)d_job, 1, 1, nullptr, c->st));
+    LAUNCH(c, launch_gather_scatter((const GatherJob*)d_job, 1, 1, (uint32_t)s->npix, (uint32_t)pb, (uint32_t*)d_gcnt, nullptr, c->st));
+    c->launches++;
     CK(c, cudaStreamSynchronize(c->st));
     if (applied_pixels) *applied_pixels = h_cnt;
     return RBF_OK;

@@ -3,35 +3,67 @@
 
 // ------------------------------------------------------------------------------------------
 // N1 / N2: ordered gather of the changed pixels' values (ivc:810-842) and the scatter
-// that rebuilds the next frame (ivc:849-909).  One CTA per pair walks the mask words in order;
-// a block scan of the popcounts gives every set pixel its rank.
+// that rebuilds the next frame (ivc:849-909).  A pair is cut into `chunks` runs of mask words; a
+// first pass counts the set bits of every chunk, then one CTA per (chunk, pair) walks its words in
+// order: rank of a set pixel = set bits of the earlier chunks + block scan of the popcounts.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_gather_scatter(const GatherJob* __restrict__ jobs, int scatter,
-                                                          uint32_t* __restrict__ counts) {
-    const GatherJob J = jobs[blockIdx.x];
+constexpr int GS_MAX_CHUNKS = 64;
+
+__global__ void __launch_bounds__(256) k_mask_chunk_count(const GatherJob* __restrict__ jobs, uint32_t chunks, uint32_t* __restrict__ counts) {
+    const GatherJob& J = jobs[blockIdx.y];
+    __shared__ uint32_t s_c[8];
+    const uint32_t nwords = (J.npix + 31u) >> 5;
+    const uint32_t w0 = (uint32_t)(((uint64_t)nwords * blockIdx.x) / chunks), w1 = (uint32_t)(((uint64_t)nwords * (blockIdx.x + 1)) / chunks);
+    uint32_t c = 0;
+    for (uint32_t w = w0 + threadIdx.x; w < w1; w += blockDim.x) c += __popc(__ldg(J.mask + w));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 8; i++) t += s_c[i];
+        counts[blockIdx.y * chunks + blockIdx.x] = t;
+    }
+}
+
+template <int PB>
+__device__ __forceinline__ void copy_pixel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src) {
+    if (PB == 2) { *reinterpret_cast<uint16_t*>(dst) = *reinterpret_cast<const uint16_t*>(src); return; }
+    if (PB == 6) {                                         // three 2-aligned samples
+        const uint16_t a = reinterpret_cast<const uint16_t*>(src)[0], b = reinterpret_cast<const uint16_t*>(src)[1], c = reinterpret_cast<const uint16_t*>(src)[2];
+        reinterpret_cast<uint16_t*>(dst)[0] = a; reinterpret_cast<uint16_t*>(dst)[1] = b; reinterpret_cast<uint16_t*>(dst)[2] = c;
+        return;
+    }
+#pragma unroll
+    for (int q = 0; q < PB; q++) dst[q] = src[q];          // PB = 1 or 3: all loads first, then the stores
+}
+
+template <int PB>
+__global__ void __launch_bounds__(1024) k_gather_scatter(const GatherJob* __restrict__ jobs, int scatter, uint32_t chunks,
+                                                          const uint32_t* __restrict__ counts, uint32_t* __restrict__ totals) {
+    const GatherJob J = jobs[blockIdx.y];
     __shared__ uint32_t s_warp[33];
     const uint32_t nwords = (J.npix + 31u) >> 5;
-    const uint32_t pb = J.pix_bytes;
+    const uint32_t w_begin = (uint32_t)(((uint64_t)nwords * blockIdx.x) / chunks), w_end = (uint32_t)(((uint64_t)nwords * (blockIdx.x + 1)) / chunks);
     uint32_t base = 0;
-    for (uint32_t w0 = 0; w0 < nwords; w0 += blockDim.x) {
+    for (uint32_t i = 0; i < blockIdx.x; i++) base += counts[blockIdx.y * chunks + i];   // set pixels before this chunk
+    for (uint32_t w0 = w_begin; w0 < w_end; w0 += blockDim.x) {
         const uint32_t w = w0 + threadIdx.x;
-        uint32_t m = (w < nwords) ? __ldg(J.mask + w) : 0u;
+        uint32_t m = (w < w_end) ? __ldg(J.mask + w) : 0u;
         uint32_t tot;
         uint32_t rank = base + block_excl_scan(__popc(m), s_warp, tot);
         while (m) {
             const uint32_t b = __ffs(m) - 1;
             m &= m - 1u;
             const size_t px = ((size_t)w << 5) + b;
-            if (scatter) {
-                for (uint32_t q = 0; q < pb; q++) J.out_frame[px * pb + q] = J.values[(size_t)rank * pb + q];
-            } else {
-                for (uint32_t q = 0; q < pb; q++) J.values[(size_t)rank * pb + q] = J.frame[px * pb + q];
-            }
+            if (scatter) copy_pixel<PB>(J.out_frame + px * PB, J.values + (size_t)rank * PB);
+            else copy_pixel<PB>(J.values + (size_t)rank * PB, J.frame + px * PB);
             rank++;
         }
         base += tot;
     }
-    if (threadIdx.x == 0 && counts) counts[blockIdx.x] = base;
+    if (threadIdx.x == 0 && totals && blockIdx.x == chunks - 1) totals[blockIdx.y] = base;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -353,9 +353,25 @@ static inline unsigned grid_for(size_t n, unsigned block) {
     if (g < 1) g = 1;
     return (unsigned)g;
 }
-cudaError_t launch_gather_scatter(const GatherJob* d_jobs, int F, int scatter, uint32_t* d_counts, cudaStream_t st) {
+uint32_t gather_chunks(uint32_t npix) {
+    uint32_t ch = ((npix + 31u) >> 5) / 4096u;             // >= 4 rounds of 1024 threads per chunk
+    if (ch > (uint32_t)GS_MAX_CHUNKS) ch = GS_MAX_CHUNKS;
+    return ch < 1u ? 1u : ch;
+}
+// d_counts: F * gather_chunks(npix) uint32 of scratch; d_totals (may be NULL): set pixels per pair
+cudaError_t launch_gather_scatter(const GatherJob* d_jobs, int F, int scatter, uint32_t npix, uint32_t pix_bytes, uint32_t* d_counts,
+                                  uint32_t* d_totals, cudaStream_t st) {
     if (F <= 0) return cudaSuccess;
-    k_gather_scatter<<<F, 1024, 0, st>>>(d_jobs, scatter, d_counts);
+    const uint32_t ch = gather_chunks(npix);
+    const dim3 grid(ch, (unsigned)F);
+    k_mask_chunk_count<<<grid, 256, 0, st>>>(d_jobs, ch, d_counts);
+    switch (pix_bytes) {
+    case 1: k_gather_scatter<1><<<grid, 1024, 0, st>>>(d_jobs, scatter, ch, d_counts, d_totals); break;
+    case 2: k_gather_scatter<2><<<grid, 1024, 0, st>>>(d_jobs, scatter, ch, d_counts, d_totals); break;
+    case 3: k_gather_scatter<3><<<grid, 1024, 0, st>>>(d_jobs, scatter, ch, d_counts, d_totals); break;
+    case 6: k_gather_scatter<6><<<grid, 1024, 0, st>>>(d_jobs, scatter, ch, d_counts, d_totals); break;
+    default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_median5(const void* d_in, uint32_t pix_stride, uint32_t H, uint32_t W, int sample_bytes, void* d_out, cudaStream_t st) {

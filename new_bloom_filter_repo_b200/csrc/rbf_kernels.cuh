@@ -57,7 +57,9 @@ cudaError_t launch_witness(const FrameJob* d_jobs, int F, uint32_t max_centuries
                            cudaStream_t st);
 cudaError_t launch_expand(const FrameJob* d_jobs, int F, uint32_t max_centuries, int sm_count, uint32_t* d_scratch, uint32_t* d_consumed,
                           cudaStream_t st);
-cudaError_t launch_gather_scatter(const GatherJob* d_jobs, int F, int scatter, uint32_t* d_counts, cudaStream_t st);
+uint32_t gather_chunks(uint32_t npix);
+cudaError_t launch_gather_scatter(const GatherJob* d_jobs, int F, int scatter, uint32_t npix, uint32_t pix_bytes, uint32_t* d_counts,
+                                  uint32_t* d_totals, cudaStream_t st);
 cudaError_t launch_median5(const void* d_in, uint32_t pix_stride, uint32_t H, uint32_t W, int sample_bytes, void* d_out, cudaStream_t st);
 cudaError_t launch_bitrev(uint32_t* d_words, size_t nwords, cudaStream_t st);
 cudaError_t launch_unpack_bits(const uint32_t* d_words, uint8_t* d_out, size_t nbits, cudaStream_t st);

@@ -454,7 +454,8 @@ def test_nccl_allgather_single_rank(pkg):
 
 
 # ------------------------------------------------------------------ SURVEY 8(f) N1 / N2 on the device
-@pytest.mark.parametrize("shape,dtype", [((64, 64), np.uint8), ((37, 53), np.uint8), ((270, 480), np.uint16), ((1080, 1920), np.uint8)])
+@pytest.mark.parametrize("shape,dtype", [((64, 64), np.uint8), ((37, 53), np.uint8), ((270, 480), np.uint16), ((1080, 1920), np.uint8),
+                                         ((2160, 3840), np.uint8), ((1080, 1920), np.uint16)])
 def test_gather_changed_and_apply_diff_vs_oracle(pkg, shape, dtype):
     from oracle import rbf_oracle as po
     frames = synth_stream(shape[0], shape[1], 4, 77, [0.05, 0.3, 0.0], dtype)
@@ -796,3 +797,21 @@ def test_inter_payload_v1_still_decodes_and_corruption_raises(pkg):
         comp.decompress_video(compressed_frames=[pls[0], pls[1], bytes(bad)])
     with pytest.raises(ValueError):
         comp.decompress_video(compressed_frames=[pls[1]])
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+def test_single_channel_frames_mask_gather_apply(pkg, dtype):
+    """Grayscale branch of _calculate_frame_diff / _apply_frame_diff (ivc:796-798, ivc:843, ivc:897-905): 1 and 2 bytes per pixel."""
+    from oracle import rbf_oracle as po
+    rng = np.random.default_rng(91)
+    hi = 256 if dtype == np.uint8 else 65536
+    prev = rng.integers(0, hi, (211, 333)).astype(dtype)
+    curr = prev.copy()
+    ch = rng.random(prev.shape) < 0.07
+    curr[ch] = (curr[ch].astype(np.int64) + hi // 4) % hi
+    vfc = pkg.VideoFrameCompressor()
+    mask, changed, dens = vfc._calculate_frame_diff(prev, curr, threshold=3.0)
+    om = po.frame_diff_mask(prev, curr, 3.0)
+    assert np.array_equal(mask, om) and changed.dtype == dtype
+    assert np.array_equal(changed, curr[np.where(om == 1)])
+    assert np.array_equal(vfc._apply_frame_diff(prev, mask, changed), curr)
