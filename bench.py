@@ -45,21 +45,31 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------ synthetic stream
-def fill_stream(frames: np.ndarray, seed: int, one_in: int = 20) -> None:
-    """frames[t] = frames[t-1] with Bernoulli(1/one_in) pixels having Y,U,V += 64 (mod 256)."""
-    nfr, h, w, _ = frames.shape
+def first_frame(h, w, seed, dtype):
     rng = np.random.default_rng(seed)
+    if np.dtype(dtype) == np.uint16:                 # BASELINE configs[4]: 16-bit samples over the whole range (int16 wrap in the diff)
+        return rng.integers(0, 65536, (h, w, 3), dtype=np.uint16)
     yy, xx = np.mgrid[0:h, 0:w]
     base = ((yy * 3 + xx * 2) % 240).astype(np.uint8)
-    frames[0, :, :, 0] = base
-    frames[0, :, :, 1] = base // 2 + 7
-    frames[0, :, :, 2] = base // 3 + 90
-    frames[0] += rng.integers(0, 8, (h, w, 3), dtype=np.uint8)
+    f0 = np.empty((h, w, 3), dtype=np.uint8)
+    f0[:, :, 0] = base
+    f0[:, :, 1] = base // 2 + 7
+    f0[:, :, 2] = base // 3 + 90
+    f0 += rng.integers(0, 8, (h, w, 3), dtype=np.uint8)
+    return f0
+
+
+def fill_stream(frames: np.ndarray, seed: int, one_in: int = 20) -> None:
+    """frames[t] = frames[t-1] with Bernoulli(1/one_in) pixels having Y,U,V += 64 (mod 256)  [16-bit: += 16384 (mod 65536)]."""
+    nfr, h, w, _ = frames.shape
+    dt = frames.dtype
+    step = dt.type(64 if dt == np.uint8 else 16384)
+    frames[0] = first_frame(h, w, seed, dt)
     from concurrent.futures import ThreadPoolExecutor
 
     def delta(t):                                    # independent of the other frames: generated in parallel
         r = np.random.default_rng(seed + t)
-        return (r.integers(0, one_in, (h, w), dtype=np.uint8) == 0).view(np.uint8) * np.uint8(64)
+        return (r.integers(0, one_in, (h, w), dtype=np.uint8) == 0).astype(dt) * step
 
     workers = max(1, min(16, (os.cpu_count() or 2) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
     with ThreadPoolExecutor(workers) as ex:
@@ -311,23 +321,18 @@ def bind_near_gpu(gpu_index: int) -> bool:
 
 def stream_frames(F, H, W, seed, lo, hi, out):
     """Frames [lo, hi] of fill_stream(F-frame stream, seed) written to out[0 .. hi-lo] without building the whole stream:
-    frame t = frame 0 + sum of the deltas 1..t (uint8 arithmetic wraps, so the sum may be taken in any order)."""
+    frame t = frame 0 + sum of the deltas 1..t (unsigned arithmetic wraps, so the sum may be taken in any order)."""
     from concurrent.futures import ThreadPoolExecutor
-    rng = np.random.default_rng(seed)
-    yy, xx = np.mgrid[0:H, 0:W]
-    base = ((yy * 3 + xx * 2) % 240).astype(np.uint8)
-    f0 = np.empty((H, W, 3), dtype=np.uint8)
-    f0[:, :, 0] = base
-    f0[:, :, 1] = base // 2 + 7
-    f0[:, :, 2] = base // 3 + 90
-    f0 += rng.integers(0, 8, (H, W, 3), dtype=np.uint8)
+    dt = out.dtype
+    step = dt.type(64 if dt == np.uint8 else 16384)
+    f0 = first_frame(H, W, seed, dt)
 
     def delta(t):
         r = np.random.default_rng(seed + t)
-        return (r.integers(0, 20, (H, W), dtype=np.uint8) == 0).view(np.uint8) * np.uint8(64)
+        return (r.integers(0, 20, (H, W), dtype=np.uint8) == 0).astype(dt) * step
 
     workers = max(1, min(16, (os.cpu_count() or 2) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
-    acc = np.zeros((H, W), dtype=np.uint8)
+    acc = np.zeros((H, W), dtype=dt)
     with ThreadPoolExecutor(workers) as ex:
         for t0 in range(1, lo + 1, 32):                    # fold the deltas before the shard into one offset
             for d in ex.map(delta, range(t0, min(lo + 1, t0 + 32))):
@@ -373,6 +378,8 @@ def run_ours(args):
     info = cabi.device_info()
     H, W, F = args.height, args.width, args.frames
     n = H * W
+    DT = np.uint16 if args.dtype == "u16" else np.uint8
+    bpp = 2 * 3 * np.dtype(DT).itemsize                   # both frames of the pair, 6 B (8-bit) / 12 B (16-bit) per pixel
     strong = args.scaling == "strong" and world > 1
     cabi.check(L.rbf_set_option(ctx, b"k1_variant", args.k1_variant), ctx)
     cabi.check(L.rbf_set_option(ctx, b"query_variant", args.query_variant), ctx)
@@ -384,14 +391,21 @@ def run_ours(args):
         pairs = hi - lo
         slots_per_rank = -(-(F - 1) // world)             # every rank contributes the same number of slots
         nfr = pairs + 1
-        frames, pin = pinned_array(cabi, (nfr, H, W, 3))
+        frames, pin = pinned_array(cabi, (nfr, H, W, 3), DT)
         stream_frames(F, H, W, 3, lo, hi, frames)
     else:                                                 # weak: one F-frame stream per rank
         lo, pairs, slots_per_rank, nfr = 0, F - 1, F - 1, F
-        frames, pin = pinned_array(cabi, (F, H, W, 3))
+        frames, pin = pinned_array(cabi, (F, H, W, 3), DT)
         fill_stream(frames, seed=3 + 1000 * rank)
-    st = pkg.FrameStream(H, W, 3, np.uint8, max_frames=nfr, max_pairs=max(pairs, slots_per_rank))
-    st.upload(frames)
+    enc = None
+    if strong:                                            # the product entry point for a sharded stream
+        enc = rdist.ShardedStreamEncoder(dist, H, W, 3, DT, F, gather=args.gather)
+        assert (enc.layout["lo"], enc.layout["pairs"], enc.layout["slots"]) == (lo, pairs, slots_per_rank)
+        st = enc.stream
+        enc.upload(frames)
+    else:
+        st = pkg.FrameStream(H, W, 3, DT, max_frames=nfr, max_pairs=max(pairs, slots_per_rank))
+        st.upload(frames)
 
     def barrier():
         if dist is not None:
@@ -401,8 +415,16 @@ def run_ours(args):
     # multi-GPU: one all-gather of the packed bit arrays per step
     send = recv = peer = None
     slot = 0
-    res = st.encode_consecutive(nfr, 3.0)
-    if world > 1:
+    kw = {}
+    res = enc.encode(3.0) if enc is not None else st.encode_consecutive(nfr, 3.0)
+    if args.k_star:                                       # BASELINE configs[4]: explicit k*, l = int(p*n*k*/ln2)
+        import math
+        kw = {"k_override": [float(args.k_star)] * pairs,
+              "l_override": [int((np.uint64(r.ones) / n) * n * args.k_star / math.log(2)) for r in res[:pairs]]}
+        res = enc.encode(3.0, **kw) if enc is not None else st.encode_consecutive(nfr, 3.0, **kw)
+    if enc is not None:
+        slot = enc.slot
+    elif world > 1:
         slot = rdist.agree_slot_bytes(dist, max(r.l for r in res))
         if args.gather == "p2p":                      # slots stored straight into every rank's buffer over NVLink peer memory
             peer = rdist.PeerGather(dist, slots_per_rank, slot)
@@ -412,7 +434,9 @@ def run_ours(args):
             recv = rdist.DeviceBuffer(slot * slots_per_rank * world)
 
     def step():
-        r = st.encode_consecutive(nfr, 3.0)
+        if enc is not None:
+            return enc.encode(3.0, **kw)
+        r = st.encode_consecutive(nfr, 3.0, **kw)
         if peer is not None:
             peer.exchange(st)
         elif world > 1:
@@ -443,7 +467,10 @@ def run_ours(args):
     # (2) N > 1: every received slot equals the owner's bit array
     gather_check = strong_check = None
     if world > 1 and args.verify_gather:
-        got = peer.result() if peer is not None else recv.to_host().reshape(world, slots_per_rank, slot)
+        if enc is not None:
+            got = enc._peer.result() if enc._peer is not None else enc._recv.to_host().reshape(world, slots_per_rank, slot)
+        else:
+            got = peer.result() if peer is not None else recv.to_host().reshape(world, slots_per_rank, slot)
         own = [hashlib.sha256(np.pad(own_bm[t][0], (0, slot))[:slot].tobytes()).hexdigest() for t in range(pairs)]
         table = [None] * world
         dist.all_gather_object(table, own)
@@ -453,14 +480,19 @@ def run_ours(args):
         flags = [None] * world
         dist.all_gather_object(flags, gather_check)
         gather_check = all(flags)
+        hdrs = enc.headers() if enc is not None else None     # collective: every rank calls it
         if strong and rank == 0:                      # (3) the gathered set == a single-GPU encode of the same F-frame stream
-            full = np.empty((F, H, W, 3), dtype=np.uint8)
+            full = np.empty((F, H, W, 3), dtype=DT)
             fill_stream(full, seed=3)
-            st1 = pkg.FrameStream(H, W, 3, np.uint8, max_frames=F)
+            st1 = pkg.FrameStream(H, W, 3, DT, max_frames=F)
             st1.upload(full)
             r1 = st1.encode_consecutive(F, 3.0)
-            flat = [got[r, t] for r in range(world) for t in range(len(table[r]))]
-            strong_check = len(flat) == F - 1
+            if args.k_star:
+                import math
+                r1 = st1.encode_consecutive(F, 3.0, k_override=[float(args.k_star)] * (F - 1),
+                                            l_override=[int((np.uint64(r.ones) / n) * n * args.k_star / math.log(2)) for r in r1])
+            flat = enc.gathered()                           # stream order, through the product's own accessor
+            strong_check = len(flat) == F - 1 and [h[0] for h in hdrs] == [r.l for r in r1]
             for t in range(F - 1):
                 bm1 = st1.fetch(t, want_mask=False)[0]
                 strong_check = strong_check and bool(np.array_equal(np.pad(bm1, (0, slot))[:slot], flat[t]))
@@ -480,14 +512,18 @@ def run_ours(args):
     stage = {k_: v / args.steps for k_, v in stage_acc.items()}
 
     # ---- end to end: host frames -> C-ABI call -> packed outputs on the host, copies inside the timed region
-    bm_slot = (max((r.l + 7) // 8 for r in res) + 15) // 16 * 16
-    wt_slot = (max((r.wlen + 7) // 8 for r in res) + 15) // 16 * 16
+    bm_slot = n // 8 if args.k_star else (max((r.l + 7) // 8 for r in res) + 15) // 16 * 16
+    wt_slot = n // 8 if args.k_star else (max((r.wlen + 7) // 8 for r in res) + 15) // 16 * 16
     out_bm, pin_bm = pinned_array(cabi, (pairs, bm_slot))
     out_wt, pin_wt = pinned_array(cabi, (pairs, wt_slot))
     e2e_steps = max(1, args.e2e_steps)
     st.encode_host(frames, 3.0, bitmap_slot=bm_slot, witness_slot=wt_slot, out_bitmaps=out_bm, out_witness=out_wt)
-    e2e_ok = all(np.array_equal(out_bm[t, :own_bm[t][0].size], own_bm[t][0]) and
-                 np.array_equal(out_wt[t, :own_bm[t][1].size], own_bm[t][1]) for t in range(pairs))
+    r_e2e = st.encode_host(frames, 3.0, bitmap_slot=bm_slot, witness_slot=wt_slot, out_bitmaps=out_bm, out_witness=out_wt)
+    if args.k_star:                                       # the host-buffer call derives (k, l) itself: checked by its own round trip
+        e2e_ok = not bool(st.decode_verify().any())
+    else:
+        e2e_ok = all(np.array_equal(out_bm[t, :own_bm[t][0].size], own_bm[t][0]) and
+                     np.array_equal(out_wt[t, :own_bm[t][1].size], own_bm[t][1]) for t in range(pairs))
     barrier()
     cabi.check(L.rbf_reset_counters(ctx), ctx)
     cabi.check(L.rbf_timer_start(ctx), ctx)
@@ -506,6 +542,35 @@ def run_ours(args):
     e2e_value = total_px / (e2e_ms * 1e-3) / 1e6
     clocks = sampler.stop()            # sampled from the first warm-up step to the end of the e2e region
 
+    # ---- the same call for a caller that holds the planar Y (the reference's yuv_info['y_plane'], fvc:289-300): the mask only
+    # needs Y, so a 1-channel stream moves a third of the bytes and produces the same bitmaps / witnesses
+    ey = None
+    if not args.k_star and not args.no_y_plane:
+        yframes, pin_y = pinned_array(cabi, (nfr, H, W), DT)
+        np.copyto(yframes, frames[:, :, :, 0])
+        sty = pkg.FrameStream(H, W, 1, DT, max_frames=nfr, max_pairs=pairs)
+        sty.encode_host(yframes, 3.0, bitmap_slot=bm_slot, witness_slot=wt_slot, out_bitmaps=out_bm, out_witness=out_wt)
+        y_ok = all(np.array_equal(out_bm[t, :own_bm[t][0].size], own_bm[t][0]) and
+                   np.array_equal(out_wt[t, :own_bm[t][1].size], own_bm[t][1]) for t in range(pairs))
+        barrier()
+        cabi.check(L.rbf_reset_counters(ctx), ctx)
+        cabi.check(L.rbf_timer_start(ctx), ctx)
+        ysteps = max(1, e2e_steps // 2)
+        for _ in range(ysteps):
+            sty.encode_host(yframes, 3.0, bitmap_slot=bm_slot, witness_slot=wt_slot, out_bitmaps=out_bm, out_witness=out_wt)
+        ms3 = C.c_double()
+        cabi.check(L.rbf_timer_stop_ms(ctx, C.byref(ms3)), ctx)
+        y_ms = ms3.value / ysteps
+        if dist is not None:
+            import torch
+            t = torch.tensor([y_ms], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            y_ms = float(t.item())
+        ey = {"value": total_px / (y_ms * 1e-3) / 1e6, "unit": "Mpixels/s", "ms_per_step": y_ms, "steps": ysteps,
+              "h2d_bytes_per_step": int(L.rbf_get_counter(ctx, b"h2d_bytes")) // ysteps, "outputs_equal_yuv444_path": bool(y_ok),
+              "api": "rbf_stream_encode_host on a 1-channel stream (planar Y in, same packed outputs)"}
+        sty.close()
+
     # a plain pinned H2D copy of the same frames: what the link itself gives this rank (the e2e ceiling)
     cabi.check(L.rbf_sync(ctx), ctx)
     t0 = time.perf_counter()
@@ -523,7 +588,7 @@ def run_ours(args):
             ncoded = sum(1 for r in res if not r.raw)
             traffic = kc["dram_bytes_per_pair"] * ncoded
             issue_frac, inst_px = kc.get("issue_active_frac"), kc.get("thread_inst_per_px")
-        achieved = coded_px * BYTES_PER_PIXEL / (q_ms * 1e-3) / 1e9
+        achieved = coded_px * bpp / (q_ms * 1e-3) / 1e9
         # (4) bitmap + witness of three pairs against the C oracle on the same frames
         oracle_ok = None
         if not args.no_cpu:
@@ -532,7 +597,7 @@ def run_ours(args):
 
             def against_oracle(t):
                 m, ones = co.frame_diff_mask(frames[t], frames[t + 1], 3.0)
-                ob, ow, *_rest = co.compress(m.reshape(-1))
+                ob, ow, *_rest = co.compress(m.reshape(-1), k_l_override=((kw["k_override"][t], kw["l_override"][t]) if kw else None))
                 return (ones == res[t].ones and np.array_equal(own_bm[t][0], np.packbits(ob)) and
                         np.array_equal(own_bm[t][1], np.packbits(ow)))
             picks = sorted({0, pairs // 2, pairs - 1})
@@ -541,10 +606,12 @@ def run_ours(args):
         parity = bool(roundtrip_ok and e2e_ok and (oracle_ok is not False) and (gather_check is not False) and
                       (strong_check is not False))
         line = {
-            "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if (H, W, args.dtype) == (2160, 3840, "u8") else "Mpixels/s bloom insert+query, %dx%d YUV444 %s inter-frame" % (W, H, args.dtype),
+            "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "4K (3840x2160) YUV444 %d-frame synthetic stream -> %s, p=0.05, "
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": ("4K (3840x2160)" if (H, W) == (2160, 3840) else "%dx%d" % (W, H)) + (" 16-bit" if DT == np.uint16 else "") +
+                                   (" k*=%g" % args.k_star if args.k_star else "") + " YUV444 %d-frame synthetic stream -> %s, p=0.05, "
                                    "threshold=3.0, seeds 0x12345678/0x87654321/999 (BASELINE configs[%s]%s)" %
                                    (F, ("%d inter-frame pairs block-partitioned over %d GPUs (%d on rank 0)" % (F - 1, world, pairs)) if strong
                                     else "%d inter-frame pairs per GPU" % pairs, "3" if strong else "2",
@@ -561,17 +628,18 @@ def run_ours(args):
                        "mean_l_bits": float(np.mean([r.l for r in res])), "mean_witness_bits": float(np.mean([r.wlen for r in res]))},
             "roofline": {"bound": "hbm", "kernel": qkernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": coded_px * BYTES_PER_PIXEL, "launch_ms": q_ms,
-                         "pipeline_frac": value * 1e6 * BYTES_PER_PIXEL / 1e9 / world / peak,
+                         "algorithmic_bytes_per_launch": coded_px * bpp, "algorithmic_bytes_per_px": bpp, "launch_ms": q_ms,
+                         "pipeline_frac": value * 1e6 * bpp / 1e9 / world / peak,
                          "issue_frac": issue_frac, "thread_inst_per_px": inst_px,
                          "counters_source": (None if kc is None else ("profiles/r02_%s_counters.json%s" % (qkernel, " (STALE: kernel sources changed)" if kc["stale"] else ""))),
-                         "note": "6 B/px counts both frames of a pair; consecutive pairs share a frame through L2, DRAM traffic of K1 is ~3.2 B/px",
+                         "note": "6 B/px (12 at 16 bit) counts both frames of a pair; consecutive pairs share a frame through L2, DRAM traffic of K1 is ~3.2 B/px",
                          "stage_ms": stage},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "steps": e2e_steps, "pcie_gbs": (h2d + d2h) / (e2e_ms * 1e-3) / 1e9,
                     "pcie_h2d_copy_gbs": pcie_peak, "pcie_frac_of_plain_copy": h2d / (e2e_ms * 1e-3) / 1e9 / pcie_peak,
-                    "api": "rbf_stream_encode_host (pinned host frames in, packed bitmaps + witnesses out)"},
+                    "api": "rbf_stream_encode_host (pinned host frames in, packed bitmaps + witnesses out)",
+                    "y_plane_only": ey},
             "gpu_launches": launches,
             "device": info["name"],
         }
@@ -610,6 +678,7 @@ def main():
     ap.add_argument("--k1-variant", type=int, default=0)
     ap.add_argument("--query-variant", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-y-plane", action="store_true", help="skip the planar-Y end-to-end measurement")
     ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"], help="N > 1: ncclAllGather, or the library's peer-memory push kernel")
     ap.add_argument("--no-verify-gather", dest="verify_gather", action="store_false",
                     help="N > 1: skip the post-run comparison of every received slot with its owner's bit array")
@@ -618,6 +687,8 @@ def main():
                     help="N > 1: weak = one --frames stream per rank; strong = ONE --frames stream block-partitioned over the ranks "
                          "(BASELINE configs[3]), every rank ends up with all bit arrays, rank 0 re-encodes the stream alone and compares")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--dtype", default="u8", choices=["u8", "u16"], help="sample type of the synthetic YUV444 stream (u16: BASELINE configs[4])")
+    ap.add_argument("--k-star", type=float, default=None, help="explicit k* with l = int(p*n*k*/ln2) instead of _calculate_optimal_params")
     ap.add_argument("--ranges", type=int, default=None, help="split each encode into this many pipelined ranges (library default if unset)")
     ap.add_argument("--no-full-frame-check", dest="full_frame_check", action="store_false",
                     help="CPU baseline: skip the full-frame (n = H*W) calibration sample")

@@ -24,6 +24,23 @@ def shard_pairs(pairs: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard_layout(total_pairs: int, rank: int, world: int) -> dict:
+    """Block partition of ONE stream's pairs over the ranks (strong scaling): rank r codes pairs [lo, hi), for which
+    it needs frames lo .. hi (one halo frame: its first `prev`); every rank contributes the same number of all-gather slots
+    (`slots` = ceil(total_pairs / world); a rank with fewer pairs leaves its last slot unused)."""
+    lo, hi = shard_pairs(total_pairs, rank, world)
+    return {"lo": lo, "hi": hi, "pairs": hi - lo, "first_frame": lo, "frames": hi - lo + 1, "slots": -(-int(total_pairs) // int(world))}
+
+
+def gathered_pair_rows(total_pairs: int, world: int):
+    """(rank, slot) of every pair 0 .. total_pairs-1 inside the gathered buffer [world][slots][slot_bytes]."""
+    rows = []
+    for r in range(world):
+        lo, hi = shard_pairs(total_pairs, r, world)
+        rows += [(r, t) for t in range(hi - lo)]
+    return rows
+
+
 def broadcast_unique_id(dist, make_id) -> np.ndarray:
     """Rank 0 calls make_id() -> uint8[128]; every rank returns the same 128 bytes (torch.distributed broadcast)."""
     import torch
@@ -142,3 +159,82 @@ class PeerGather:
             L.rbf_peer_close(ctx, p)
         self._opened = []
         self.recv.free(); self.flags.free()
+
+
+class ShardedStreamEncoder:
+    """One caller stream of `total_frames` frames coded by all ranks together (BASELINE configs[3], strong scaling): each rank
+    uploads frames first_frame .. first_frame+frames-1 of the stream (its block plus the halo frame), `encode` runs the hot path
+    on the block and exchanges the packed bit arrays with ONE all-gather, after which every rank holds the bit array of every
+    pair of the stream.  The per-pair headers (l, |w|, p, k, ones, raw) travel as a small object gather next to it."""
+
+    def __init__(self, dist, height: int, width: int, channels: int, dtype, total_frames: int, gather: str = "nccl"):
+        from .stream import FrameStream
+        self.dist = dist
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.total_pairs = int(total_frames) - 1
+        self.layout = shard_layout(self.total_pairs, self.rank, self.world)
+        self.gather = gather
+        self.stream = FrameStream(height, width, channels, dtype, max_frames=self.layout["frames"],
+                                  max_pairs=max(self.layout["pairs"], self.layout["slots"]))
+        self.slot = 0
+        self._send = self._recv = self._peer = None
+        self._nccl_ready = False
+        self.results = None
+
+    def upload(self, frames_of_this_rank: np.ndarray) -> None:
+        if frames_of_this_rank.shape[0] != self.layout["frames"]:
+            raise ValueError("rank %d codes frames %d..%d of the stream: %d frames expected" %
+                             (self.rank, self.layout["first_frame"], self.layout["first_frame"] + self.layout["frames"] - 1, self.layout["frames"]))
+        self.stream.upload(frames_of_this_rank)
+
+    def _ensure_buffers(self, max_l_bits: int) -> None:
+        need = agree_slot_bytes(self.dist, max_l_bits)
+        if need <= self.slot:
+            return
+        if self._peer is not None:
+            self._peer.close(self.dist)
+        for b in (self._send, self._recv):
+            if b is not None:
+                b.free()
+        self.slot = need
+        n = self.layout["slots"]
+        if self.gather == "p2p":
+            self._peer = PeerGather(self.dist, n, self.slot)
+        else:
+            if not self._nccl_ready:
+                init_nccl_from_torch(self.dist)
+                self._nccl_ready = True
+            self._send = DeviceBuffer(self.slot * n)
+            self._recv = DeviceBuffer(self.slot * n * self.world)
+
+    def encode(self, threshold: float, **kw):
+        """Code this rank's block and enqueue the exchange (it overlaps the next encode; complete after `gathered()` / rbf_sync)."""
+        self.results = self.stream.encode_consecutive(self.layout["frames"], threshold, **kw)
+        if self.slot == 0 or max(r.l for r in self.results) > 8 * self.slot:
+            self._ensure_buffers(max(r.l for r in self.results))
+        if self._peer is not None:
+            self._peer.exchange(self.stream)
+        else:
+            _cabi.check(_cabi.lib().rbf_stream_allgather_bitmaps(self.stream._h, self.layout["slots"], self.slot, self._send.ptr,
+                                                                 self._recv.ptr), _cabi.ctx())
+        return self.results
+
+    def gathered(self) -> np.ndarray:
+        """uint8[total_pairs, slot]: the packbits bit array of every pair of the stream, in stream order (host copy)."""
+        got = self._peer.result() if self._peer is not None else self._recv.to_host().reshape(self.world, self.layout["slots"], self.slot)
+        return np.stack([got[r, t] for r, t in gathered_pair_rows(self.total_pairs, self.world)])
+
+    def headers(self):
+        """Per pair of the whole stream: (l, wlen, p, k, ones, raw) gathered from the owners."""
+        mine = [(r.l, r.wlen, r.p, r.k, r.ones, r.raw) for r in self.results[: self.layout["pairs"]]]
+        table = [None] * self.world
+        self.dist.all_gather_object(table, mine)
+        return [h for part in table for h in part]
+
+    def close(self) -> None:
+        if self._peer is not None:
+            self._peer.close(self.dist)
+        for b in (self._send, self._recv):
+            if b is not None:
+                b.free()
+        self.stream.close()

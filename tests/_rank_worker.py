@@ -17,7 +17,14 @@ def main():
     lo, hi = rdist.shard_pairs(pairs, rank, world)
     ident = rdist.broadcast_unique_id(dist, lambda: (np.arange(128) * 7 + 3).astype(np.uint8))
     slot = rdist.agree_slot_bytes(dist, 1000 + 777 * rank)
-    out = {"rank": rank, "world": world, "lo": lo, "hi": hi, "id_sum": int(ident.sum()), "id0": int(ident[1]), "slot": slot}
+    # strong-scaling layout: per-rank header lists gathered as objects, rows of the gathered slot buffer in stream order
+    lay = rdist.shard_layout(pairs, rank, world)
+    table = [None] * world
+    dist.all_gather_object(table, [(lay["lo"] + t, rank) for t in range(lay["pairs"])])
+    headers = [h for part in table for h in part]
+    rows = rdist.gathered_pair_rows(pairs, world)
+    out = {"rank": rank, "world": world, "lo": lo, "hi": hi, "id_sum": int(ident.sum()), "id0": int(ident[1]), "slot": slot,
+           "layout": lay, "headers": headers, "rows": rows}
     with open(os.path.join(sys.argv[2], "rank%d.json" % rank), "w") as f:
         json.dump(out, f)
     dist.barrier()

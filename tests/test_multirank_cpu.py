@@ -35,3 +35,9 @@ def test_world_size_2_gloo(tmp_path):
     assert all(o["id_sum"] == int(expect.sum()) and o["id0"] == int(expect[1]) for o in outs)
     want_slot = ((1000 + 777 + 7) // 8 + 15) // 16 * 16
     assert all(o["slot"] == want_slot for o in outs)
+    # strong-scaling layout (ShardedStreamEncoder's host logic): equal slot counts, one halo frame, stream-ordered rows
+    for o in outs:
+        lay = o["layout"]
+        assert lay["slots"] == 15 and lay["frames"] == lay["pairs"] + 1 and lay["first_frame"] == lay["lo"] == o["lo"]
+        assert [h[0] for h in o["headers"]] == list(range(pairs))
+        assert [tuple(r) for r in o["rows"]] == [(h[1], h[0] - outs[h[1]]["lo"]) for h in o["headers"]]
