@@ -1292,7 +1292,7 @@ extern "C" int rbf_stream_allgather_bitmaps(rbf_stream* s, uint32_t pairs, uint6
     if (!s || !d_recv) return set_err(s ? s->c : nullptr, RBF_ERR_INVALID, "rbf_stream_allgather_bitmaps: NULL");
     rbf_ctx* c = s->c;
     const size_t stride = s->mask_stride_w * 4;
-    if (slot_bytes == 0 || slot_bytes > stride || (slot_bytes & 3) || pairs == 0 || pairs > s->max_pairs)
+    if (slot_bytes == 0 || slot_bytes > stride || (slot_bytes & 15) || pairs == 0 || pairs > s->max_pairs)
         return set_err(c, RBF_ERR_INVALID, "bad slot/pairs");
     if (c->peer_nranks > 0) {
         // peer-memory exchange: one kernel stores this rank's slots into every rank's receive buffer over NVLink

@@ -233,12 +233,14 @@ struct PeerTable {
 
 __global__ void __launch_bounds__(256) k_push_slots(const uint32_t* __restrict__ bits, size_t stride_w, uint32_t slot_w, uint32_t pairs,
                                                     PeerTable pt, int nranks, size_t dst_off_w) {
-    const size_t total = (size_t)pairs * slot_w;
+    // 16-byte granules: slot_w and stride_w are multiples of 4 words and every buffer is 16 B aligned (checked by the host)
+    const uint32_t slot_q = slot_w >> 2;
+    const size_t total = (size_t)pairs * slot_q;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t pair = (uint32_t)(i / slot_w), w = (uint32_t)(i - (size_t)pair * slot_w);
-        const uint32_t v = __ldg(bits + (size_t)pair * stride_w + w);
+        const uint32_t pair = (uint32_t)(i / slot_q), q = (uint32_t)(i - (size_t)pair * slot_q);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(bits + (size_t)pair * stride_w) + q);
 #pragma unroll 1
-        for (int r = 0; r < nranks; r++) pt.recv[r][dst_off_w + i] = v;
+        for (int r = 0; r < nranks; r++) reinterpret_cast<uint4*>(pt.recv[r] + dst_off_w)[i] = v;   // peer address: an NVLink write
     }
 }
 // after k_push_slots on the same stream: tell every rank that this rank's slots of exchange `seq` have landed

@@ -441,7 +441,8 @@ cudaError_t launch_push_slots(const uint32_t* d_bits, size_t stride_w, uint32_t 
     if (nranks < 1 || nranks > PEER_MAX) return cudaErrorInvalidValue;
     PeerTable pt;
     for (int r = 0; r < PEER_MAX; r++) { pt.recv[r] = r < nranks ? recv[r] : nullptr; pt.flags[r] = r < nranks ? flags[r] : nullptr; }
-    const size_t total = (size_t)pairs * slot_w;
+    if ((slot_w & 3u) || (stride_w & 3u) || (dst_off_w & 3u)) return cudaErrorInvalidValue;
+    const size_t total = (size_t)pairs * (slot_w >> 2);
     size_t grid = (total + 255) / 256;
     if (grid > (size_t)sm_count * 8) grid = (size_t)sm_count * 8;
     if (grid < 1) grid = 1;
