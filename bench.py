@@ -581,7 +581,7 @@ def run_ours(args):
         peak, peak_src = measured_peaks()
         q_ms = stage["k3_query"]
         coded_px = sum(r.n for r in res if not r.raw)
-        qkernel = "k_query3" if args.query_variant == 4 else "k_query2"
+        qkernel = {4: "k_query3", 5: "k_query4", 6: "k_query4"}.get(args.query_variant, "k_query2")
         kc = kernel_counters(qkernel)
         traffic = issue_frac = inst_px = None
         if kc is not None and not kc["stale"]:
@@ -624,7 +624,8 @@ def run_ours(args):
                                   "c_oracle_pairs_0_mid_last": oracle_ok},
                        "l2_policy": "inputs larger than L2: %.2f GB of frames per step, no flush needed" % (nfr * n * 3 / 1e9),
                        "k1_variant": "tma-bulk-ring" if args.k1_variant == 1 else "ldg256", "rank_bound_to_gpu_numa_node": numa_bound,
-                       "query_variant": {0: "per-lane", 1: "staged-rings", 2: "staged-rings+dsmem-cluster", 3: "dense-A+B", 4: "decade-tiles"}.get(args.query_variant),
+                       "query_variant": {0: "per-lane", 1: "staged-rings", 2: "staged-rings+dsmem-cluster", 3: "dense-A+B", 4: "decade-tiles-r1",
+                                         5: "decade-tiles-carry", 6: "half-decade-tiles-carry"}.get(args.query_variant),
                        "mean_l_bits": float(np.mean([r.l for r in res])), "mean_witness_bits": float(np.mean([r.wlen for r in res]))},
             "roofline": {"bound": "hbm", "kernel": qkernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -676,7 +677,7 @@ def main():
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--k1-variant", type=int, default=0)
-    ap.add_argument("--query-variant", type=int, default=4)
+    ap.add_argument("--query-variant", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-y-plane", action="store_true", help="skip the planar-Y end-to-end measurement")
     ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"], help="N > 1: ncclAllGather, or the library's peer-memory push kernel")

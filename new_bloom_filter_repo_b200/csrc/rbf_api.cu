@@ -39,14 +39,16 @@ struct rbf_ctx {
     cudaStream_t st_k1 = nullptr;     // pipelined encode: K1 of the later ranges + the witness memset run here, beside K2 on `st`
     cudaStream_t st_d2h = nullptr;    // rbf_stream_encode_host: result copies of chunk i overlap the kernels of chunk i+1
     cudaEvent_t ev_fork = nullptr, ev_wit = nullptr, ev_k1[8] = {nullptr}, ev_d2h = nullptr;
-    int encode_ranges = 4;            // rbf_stream_encode: K1/K2 pipelined over this many ranges of pairs (1 = serial)
+    int encode_ranges = 1;            // rbf_stream_encode: K1/K2 pipelined over this many ranges of pairs (1 = serial, the default: K1 (HBM)
+                                      // and K2 (L2 atomics) slow each other down when they overlap -- profiles/r02_kbench_pipeline.jsonl)
     int k1_ctas_per_sm = 32;          // grid cap of K1 (pipelined encodes use pipe_k1_ctas_per_sm so that K2 finds room beside it)
     int pipe_k1_ctas_per_sm = 4;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaDeviceProp prop;
     int sm_count = 0;
     int k1_variant = 0;
-    int insert_variant = 2; // 2: bit array privatised in shared memory + word-wide merge; 1: dense warp-compacted K2 (RED per probe); 0: per-lane K2
+    int insert_variant = 1; // 1: dense warp-compacted K2 (one RED.OR per probe; default); 2: bit array privatised in shared memory + word-wide
+                            // merge (measured slower: shared-memory atomics at ~0.8 lane-ops/clk/SM); 0: per-lane K2
     int query_variant = 5;  // 0: per-lane; 1: staged A->B->C rings, L2 tail; 2: staged + 2-CTA DSMEM clusters; 3: dense A+B, ring before C;
                             // 4: decade tiles of round 1 (m <= 2^23, else 1); 5: decade tiles with carried stage-B batches (half tiles
                             // for 2^23 < m <= 2^24, ring kernel beyond); 6: half-decade tiles for every m <= 2^24

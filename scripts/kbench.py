@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--one-in", type=int, default=20, help="change density 1/one_in of the synthetic stream (20 -> p = 0.05)")
     ap.add_argument("--configs", default=None, help="JSON list of option dicts; default: the built-in sweep")
     args = ap.parse_args()
     import new_bloom_filter_repo_b200 as pkg
@@ -28,14 +29,13 @@ def main():
     L, ctx = cabi.lib(), cabi.ctx()
     F, H, W = args.frames, args.height, args.width
     frames, pin = bench.pinned_array(cabi, (F, H, W, 3))
-    bench.fill_stream(frames, seed=3)
+    bench.fill_stream(frames, seed=3, one_in=args.one_in)
     st = pkg.FrameStream(H, W, 3, np.uint8, max_frames=F)
     st.upload(frames)
-    base = {"query_variant": 5, "insert_variant": 2, "encode_ranges": 4, "pipe_k1_ctas_per_sm": 4}
+    base = {"query_variant": 5, "insert_variant": 1, "encode_ranges": 1, "pipe_k1_ctas_per_sm": 4, "query_smem_bytes": 0}
     sweep = json.loads(args.configs) if args.configs else [
-        {}, {"query_variant": 4}, {"query_variant": 6}, {"insert_variant": 1}, {"encode_ranges": 1},
-        {"encode_ranges": 2}, {"encode_ranges": 8}, {"pipe_k1_ctas_per_sm": 2}, {"pipe_k1_ctas_per_sm": 8},
-        {"pipe_k1_ctas_per_sm": 32}, {"query_variant": 4, "insert_variant": 1, "encode_ranges": 1},
+        {}, {"query_variant": 4}, {"query_variant": 6}, {"insert_variant": 2}, {"encode_ranges": 4},
+        {"query_smem_bytes": 200000}, {"query_smem_bytes": 170000}, {"query_smem_bytes": 140000}, {"query_smem_bytes": 110000},
     ]
     out = open(args.out, "w") if args.out else None
     ref_sha = None
