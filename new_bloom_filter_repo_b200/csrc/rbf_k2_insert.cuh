@@ -18,8 +18,11 @@ __device__ __forceinline__ FilterK filter_consts(const FrameJob& J) {
 // fast reductions for 2 <= m <= 2^30 (the specialised insert / query paths are only taken then)
 __device__ __forceinline__ uint32_t mod_fast(uint64_t h, const FastMod& f, uint32_t neg_m) {
     const uint32_t hh = (uint32_t)(h >> 32), hl = (uint32_t)h;
-    const uint32_t q = hh * f.Mh + __umulhi(hh, f.Ml) + __umulhi(hl, f.Mh);
-    uint32_t r = q * neg_m + hl;                                       // hl - q*m in one IMAD (neg_m = 2^32 - m from the host)
+    // q = hh*Mh + hi(hh*Ml) + hi(hl*Mh);  r = hl - q*m = hl + q*neg_m (neg_m = 2^32 - m from the host), with q's two parts
+    // folded into two IMADs (no add, and no zeroed register pair for an accumulating IMAD.HI)
+    uint32_t r;
+    asm("{\n .reg .u32 a, b;\n mul.hi.u32 a, %1, %4;\n mad.lo.u32 a, %1, %3, a;\n mul.hi.u32 b, %2, %3;\n mad.lo.u32 %0, b, %5, %2;\n mad.lo.u32 %0, a, %5, %0;\n}"
+        : "=&r"(r) : "r"(hh), "r"(hl), "r"(f.Mh), "r"(f.Ml), "r"(neg_m));
     r = min(r, r - 2u * f.m);
     return min(r, r - f.m);
 }
