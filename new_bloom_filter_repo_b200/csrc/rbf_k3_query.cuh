@@ -183,22 +183,6 @@ __device__ __forceinline__ uint32_t probe_bit(uint32_t sm_addr, uint32_t sm_addr
     return (word >> (idx & 31u)) & 1u;
 }
 
-// the 32-bit word that holds bit `idx` (same three probe modes as probe_bit); the caller shifts when it needs the bit, so the
-// load can be issued a whole batch ahead of its use
-template <int PM>
-__device__ __forceinline__ uint32_t probe_word(uint32_t sm_addr, const uint32_t* __restrict__ gl, uint32_t sm_words, uint32_t idx) {
-    const uint32_t w = idx >> 5;
-    uint32_t word;
-    if (PM == 1) {
-        asm volatile("{\n .reg .pred q;\n setp.lt.u32 q, %1, %2;\n mov.u32 %0, 0;\n @q ld.shared.u32 %0, [%3];\n @!q ld.global.nc.u32 %0, [%4];\n}"
-                     : "=r"(word)
-                     : "r"(w), "r"(sm_words), "r"(sm_addr + 4u * w), "l"(gl + w));
-    } else {
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(sm_addr + 4u * w));
-    }
-    return word;
-}
-
 // mod_fast / addmod_fast (exact h mod m for 2 <= m <= 2^30) live in rbf_k2_insert.cuh
 
 // pass bit of (owner lane, x, y) into the owner's 128-bit accumulator
@@ -905,54 +889,6 @@ __device__ __noinline__ void query_slab_tiled2(const FilterK K, uint32_t sm_addr
             uint32_t nproc = last_tile ? tot2 : (tot2 & ~31u);
             if (nproc == 0u && rem != 0u) nproc = tot2;              // a record is carried over one tile at most
             const uint32_t yoff = (uint32_t)(h * TY);
-            if (FKT >= 2) {
-                // Software-pipelined by one batch: iteration b hashes batch b and ISSUES its probe loads, then consumes the words
-                // that batch b-1 asked for.  The probe of a batch is one L2 round trip for the ~1/3 of the lanes whose word lies
-                // beyond the shared-memory copy; consumed in place it was 13 % of all stall samples of the kernel (ncu, r02).
-                uint32_t cw1 = 0, cw2 = 0, cmeta = 0, cidx = 0;      // batch b-1: probe words, {tag:13, bit1:5, bit2:5, have:1}, index of probe floor_k
-#pragma unroll 1
-                for (uint32_t b = 0; b < nproc + 32u; b += 32u) {
-                    uint32_t nw1 = 0, nw2 = 0, nmeta = 0, nidx = 0;
-                    if (b < nproc) {                                 // ---- produce batch b
-                        const uint32_t g = b + lane;
-                        const bool have = g < nproc;
-                        const uint32_t rec = lds32(buf_addr + 4u * min(g, (uint32_t)(Cfg::BUF - 1)));
-                        const uint32_t owner = (rec >> Cfg::IDXB) & 31u;
-                        uint32_t y = (rec >> (Cfg::IDXB + 5)) + yoff, xr = x;
-                        uint64_t D2o = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)D2, owner) |
-                                       ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(D2 >> 32), owner) << 32);
-                        if (b == 0u && rem != 0u) {                  // warp-uniform: the batch that holds the carried records
-                            const uint64_t D2q = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)D2p, owner) |
-                                                 ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(D2p >> 32), owner) << 32);
-                            if (g < rem) { D2o = D2q; y = (rec >> (Cfg::IDXB + 5)) + yoffp; xr = xp; }
-                        }
-                        if (!have) y = 0u;
-                        uint64_t rb = 0;
-                        if (kind_ends_in_byte<KIND>()) { const uint2 t = lds64(rb_addr + 8u * y); rb = (uint64_t)t.x | ((uint64_t)t.y << 32); }
-                        const uint32_t stepm = have ? mod_fast(finish_prep<KIND>(D2o, K.s2, y, rb), K.fm, K.nm) : 0u;
-                        const uint32_t i1 = addmod_fast(have ? (rec & IDXM) : 0u, stepm, K.fm.m);
-                        nw1 = probe_word<PM>(sm_addr, gl, sm_words, i1);
-                        uint32_t i2 = i1, ilast = i1;
-                        if (FKT >= 3) { i2 = addmod_fast(i1, stepm, K.fm.m); nw2 = probe_word<PM>(sm_addr, gl, sm_words, i2); ilast = i2; }
-                        nidx = addmod_fast(ilast, stepm, K.fm.m);    // index of probe floor_k
-                        nmeta = (owner << 8) | (xr << 4) | y | ((i1 & 31u) << 13) | ((i2 & 31u) << 18) | ((have ? 1u : 0u) << 23);
-                    }
-                    if (b != 0u) {                                   // ---- consume batch b-1
-                        uint32_t ok = (cmeta >> 23) & (cw1 >> ((cmeta >> 13) & 31u)) & 1u;
-                        if (FKT >= 3) ok &= cw2 >> ((cmeta >> 18) & 31u);
-                        const uint32_t tag = cmeta & 0x1fffu;
-                        if (K.has_act) {
-                            const uint32_t b2 = __ballot_sync(0xffffffffu, ok != 0u);
-                            sts64_if(qc_addr + 8u * ((qc_head + qc_cnt + __popc(b2 & lt)) & (Q2_RING - 1)), cidx, tag, ok != 0u);
-                            qc_cnt += __popc(b2);
-                            if (qc_cnt >= 32u) drain_c_ring<KIND, PM>(K, sm_addr, 0u, gl, sm_words, qc_addr, pacc_addr, lane, CA, qc_head, qc_cnt);
-                        } else {
-                            deliver_pass(pacc_addr, tag, ok != 0u);
-                        }
-                    }
-                    cw1 = nw1; cw2 = nw2; cmeta = nmeta; cidx = nidx;
-                }
-            } else {
 #pragma unroll 1
             for (uint32_t b = 0; b < nproc; b += 32u) {
                 const uint32_t g = b + lane;
@@ -973,9 +909,17 @@ __device__ __noinline__ void query_slab_tiled2(const FilterK K, uint32_t sm_addr
                 const uint32_t stepm = have ? mod_fast(finish_prep<KIND>(D2o, K.s2, y, rb), K.fm, K.nm) : 0u;
                 uint32_t idx = have ? (rec & IDXM) : 0u;
                 uint32_t ok = have ? 1u : 0u;
-                for (uint32_t i = 1; i < K.fk; i++) {
-                    idx = addmod_fast(idx, stepm, K.fm.m);
-                    ok &= probe_bit<PM>(sm_addr, 0u, gl, sm_words, idx);
+                if (FKT > 0) {
+#pragma unroll
+                    for (int i = 1; i < FKT; i++) {
+                        idx = addmod_fast(idx, stepm, K.fm.m);
+                        ok &= probe_bit<PM>(sm_addr, 0u, gl, sm_words, idx);
+                    }
+                } else {
+                    for (uint32_t i = 1; i < K.fk; i++) {
+                        idx = addmod_fast(idx, stepm, K.fm.m);
+                        ok &= probe_bit<PM>(sm_addr, 0u, gl, sm_words, idx);
+                    }
                 }
                 const uint32_t tag = (owner << 8) | (xr << 4) | y;
                 if (K.has_act) {
@@ -987,7 +931,6 @@ __device__ __noinline__ void query_slab_tiled2(const FilterK K, uint32_t sm_addr
                 } else {
                     deliver_pass(pacc_addr, tag, ok != 0u);
                 }
-            }
             }
             // ---- carry the leftover (< 32 records) to the front of the buffer
             const uint32_t nrem = tot2 - nproc;

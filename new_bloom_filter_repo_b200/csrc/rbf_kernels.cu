@@ -322,7 +322,8 @@ cudaError_t launch_query(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, 
 }
 
 static uint32_t witness_chunks(int F, uint32_t max_centuries, int sm_count) {
-    uint32_t ch = (uint32_t)((4 * sm_count + F - 1) / F);             // aim at ~4 CTAs per SM (two resident at a time)
+    uint32_t ch = (uint32_t)((16 * sm_count + F - 1) / F);            // >= 8 waves of the two 1024-thread CTAs an SM holds: at 2 waves
+                                                                      // (round 1) the ragged last wave cost up to a third of K3b
     const uint32_t by_size = max_centuries / 4096u;                   // at least 4096 centuries (4 rounds) per chunk
     if (ch > by_size) ch = by_size;
     if (ch > 32u) ch = 32u;

@@ -1,5 +1,6 @@
-"""GPU: throughput of the other BASELINE.json configs (1080p 30-frame stream; 8K 16-bit k* sweep), one JSON line each.
-Parity for these shapes is covered by tests/test_gpu_parity.py; this script only times them (CUDA events inside the library)."""
+"""GPU: throughput of the other BASELINE.json configs (1080p 30-frame stream; 8K 16-bit k* sweep) and of the N1 / N2 kernels
+(ordered gather of the changed values, scatter back), one JSON line each.  Parity for these shapes is covered by
+tests/test_gpu_parity.py; this script only times them (CUDA events inside the library)."""
 import ctypes as C, json, math, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -35,8 +36,26 @@ print(json.dumps({"config": "1080p YUV444 30 frames, 29 inter-frame pairs, p cyc
                   "Mpixels_per_s": 29 * h * w / ms / 1e3, "stage_ms": st.stage_ms(), "raw_pairs": sum(r.raw for r in res)}), flush=True)
 st.close()
 
+# ---- N1 / N2 at 4K: gather of the changed values of 16 pairs (p = 0.05) and one apply_diff, device time incl. the D2H of the values
+h, w, F = 2160, 3840, 17
+import bench as _bench
+frames = np.empty((F, h, w, 3), np.uint8)
+_bench.fill_stream(frames, seed=3)
+st = pkg.FrameStream(h, w, 3, np.uint8, max_frames=F + 1)
+st.upload(frames)
+res = st.encode_consecutive(F, 3.0)
+ms, vals = timed(st, lambda: st.gather_changed(F - 1), reps=5, warm=2)
+nbytes = sum(v.nbytes for v in vals)
+mask = np.unpackbits(st.fetch_batch(0, 1, want_masks=True)[2][0], bitorder="little")[: h * w]
+ms2, _ = timed(st, lambda: st.apply_diff(0, F, mask, vals[0]), reps=5, warm=2)
+print(json.dumps({"config": "N1 gather_changed, 4K YUV444, %d pairs, p=0.05 (incl. D2H of %.1f MB of values and the host-side offsets)" % (F - 1, nbytes / 1e6),
+                  "ms_per_call": ms, "us_per_pair": ms * 1e3 / (F - 1),
+                  "N2_apply_diff_one_4K_frame_ms (incl. H2D of mask + values, D2D frame copy)": ms2}), flush=True)
+st.close()
+
 # ---- config[4]: 8K 16-bit, 16 frames, explicit k* sweep (l = int(p*n*k/ln2))
 h, w, F = 4320, 7680, 8
+frames = None
 n = h * w
 rng = np.random.default_rng(5)
 frames = np.empty((F, h, w, 3), np.uint16)
