@@ -581,7 +581,7 @@ def run_ours(args):
         peak, peak_src = measured_peaks()
         q_ms = stage["k3_query"]
         coded_px = sum(r.n for r in res if not r.raw)
-        qkernel = {4: "k_query3", 5: "k_query4", 6: "k_query4"}.get(args.query_variant, "k_query2")
+        qkernel = {5: "k_query4", 6: "k_query4", 0: "k_query"}.get(args.query_variant, "k_query2")
         kc = kernel_counters(qkernel)
         traffic = issue_frac = inst_px = None
         if kc is not None and not kc["stale"]:
@@ -624,8 +624,7 @@ def run_ours(args):
                                   "c_oracle_pairs_0_mid_last": oracle_ok},
                        "l2_policy": "inputs larger than L2: %.2f GB of frames per step, no flush needed" % (nfr * n * 3 / 1e9),
                        "k1_variant": "tma-bulk-ring" if args.k1_variant == 1 else "ldg256", "rank_bound_to_gpu_numa_node": numa_bound,
-                       "query_variant": {0: "per-lane", 1: "staged-rings", 2: "staged-rings+dsmem-cluster", 3: "dense-A+B", 4: "decade-tiles-r1",
-                                         5: "decade-tiles-carry", 6: "half-decade-tiles-carry"}.get(args.query_variant),
+                       "query_variant": {0: "per-lane", 1: "staged-rings", 5: "decade-tiles-carry", 6: "half-decade-tiles-carry"}.get(args.query_variant),
                        "mean_l_bits": float(np.mean([r.l for r in res])), "mean_witness_bits": float(np.mean([r.wlen for r in res]))},
             "roofline": {"bound": "hbm", "kernel": qkernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

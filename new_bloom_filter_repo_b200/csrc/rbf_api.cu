@@ -47,8 +47,7 @@ struct rbf_ctx {
     cudaDeviceProp prop;
     int sm_count = 0;
     int k1_variant = 0;
-    int insert_variant = 1; // 1: dense warp-compacted K2 (one RED.OR per probe; default); 2: bit array privatised in shared memory + word-wide
-                            // merge (measured slower: shared-memory atomics at ~0.8 lane-ops/clk/SM); 0: per-lane K2
+    int insert_variant = 1; // 1: dense warp-compacted K2 (one RED.OR per probe; default); 0: per-lane K2
     int query_variant = 5;  // 0: per-lane; 1: staged A->B->C rings, L2 tail; 2: staged + 2-CTA DSMEM clusters; 3: dense A+B, ring before C;
                             // 4: decade tiles of round 1 (m <= 2^23, else 1); 5: decade tiles with carried stage-B batches (half tiles
                             // for 2^23 < m <= 2^24, ring kernel beyond); 6: half-decade tiles for every m <= 2^24
@@ -264,7 +263,7 @@ extern "C" int rbf_set_option(rbf_ctx* c, const char* key, int64_t v) {
     if (!c || !key) return set_err(c, RBF_ERR_INVALID, "rbf_set_option: NULL");
     if (!strcmp(key, "k1_variant")) { c->k1_variant = (int)v; return RBF_OK; }
     if (!strcmp(key, "query_variant")) { c->query_variant = (int)(v < 0 ? 0 : (v > 6 ? 6 : v)); return RBF_OK; }
-    if (!strcmp(key, "insert_variant")) { c->insert_variant = (int)(v < 0 ? 0 : (v > 2 ? 2 : v)); return RBF_OK; }
+    if (!strcmp(key, "insert_variant")) { c->insert_variant = v ? 1 : 0; return RBF_OK; }
     if (!strcmp(key, "host_chunk_frames")) { c->host_chunk_frames = (int)v; return RBF_OK; }
     if (!strcmp(key, "k1_only")) { c->k1_only = v ? 1 : 0; return RBF_OK; }        // default of streams created afterwards
     if (!strcmp(key, "mask_mode")) { c->mask_mode = v ? 1 : 0; return RBF_OK; }    // (per-stream: rbf_stream_set_option)

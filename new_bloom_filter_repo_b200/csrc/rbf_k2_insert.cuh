@@ -74,67 +74,92 @@ __global__ void __launch_bounds__(256) k_insert(const FrameJob* __restrict__ job
 }
 
 // ------------------------------------------------------------------------------------------
-// K2 (dense): the same insert with all lanes busy.  The mask is sparse (p ~ 5 %), so a lane
+// K2 (dense, the default): the same insert with all lanes busy.  The mask is sparse (p ~ 5 %), so a lane
 // looping over its own set positions leaves most of the warp idle.  Here a warp takes a slab of
-// 32 centuries: every lane publishes its three century states to shared memory, the set
-// positions of the slab are compacted (count, warp scan, scatter) into a per-warp item list, and
-// the list is consumed 32 items at a time: two-character finish from the owner's century state,
-// Barrett reduction, RED.OR into the bit array.
+// 32 centuries: the set positions of the slab are compacted (count, warp scan, scatter) into a
+// per-warp item list (rounds of at most I2_CAP items), and the list is consumed 32 items at a time:
+// the owner's century states come by shuffle, two-character finish, the one-IMAD remainder of the
+// query kernels, floor(k)-specialised straight-line probes, RED.OR (fire-and-forget) into the
+// L2-resident bit array.
+// (Round 2 also tried building the array in shared memory -- a private copy per CTA, merged with one RED
+// per non-zero word: 8.0 us per 4K pair against 6.8 for this kernel; shared-memory atomics on random words
+// run at < 1 lane-op per clock per SM.  profiles/r02_kbench_variants_smem_sweep.jsonl, insert_variant 2.)
 // ------------------------------------------------------------------------------------------
 constexpr int I2_WARPS = 4;
-constexpr int I2_LIST = 3200;                                        // worst case: every position of the slab set
+constexpr int I2_CAP = 512;                                           // list entries per warp and round (uint16 each)
+
+template <int KIND, int FKT>
+__device__ __forceinline__ void insert_batch(const FilterK& K, uint32_t* __restrict__ bits, uint32_t tag, bool have, uint64_t C1,
+                                             uint64_t C2, uint64_t CA) {
+    const uint32_t owner = (tag >> 7) & 31u, pos = tag & 127u, x = (pos * 205u) >> 11, y = pos - 10u * x;   // pos < 128: /10 exact
+    const uint64_t C1o = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)C1, owner) | ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(C1 >> 32), owner) << 32);
+    const uint64_t C2o = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)C2, owner) | ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(C2 >> 32), owner) << 32);
+    uint64_t CAo = 0;
+    if (K.has_act) CAo = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)CA, owner) | ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(CA >> 32), owner) << 32);
+    if (!have) return;
+    uint32_t idx = mod_fast(finish_t<KIND>(decade_state_t<KIND>(C1o, K.s1, x), K.s1, y), K.fm, K.nm);
+    const uint32_t step = mod_fast(finish_t<KIND>(decade_state_t<KIND>(C2o, K.s2, x), K.s2, y), K.fm, K.nm);
+    if (FKT > 0) {
+#pragma unroll
+        for (int p = 0; p < FKT; p++) { red_or_global(bits + (idx >> 5), 1u << (idx & 31u)); idx = addmod_fast(idx, step, K.fm.m); }
+    } else {
+        for (uint32_t p = 0; p < K.fk; p++) { red_or_global(bits + (idx >> 5), 1u << (idx & 31u)); idx = addmod_fast(idx, step, K.fm.m); }
+    }
+    if (K.has_act && finish_t<KIND>(decade_state_t<KIND>(CAo, K.sA, x), K.sA, y) < K.T) red_or_global(bits + (idx >> 5), 1u << (idx & 31u));
+}
 
 template <int KIND>
-__device__ __forceinline__ void insert_slab_dense(const FilterK& K, uint32_t* __restrict__ bits, const Bits128 mb,
-                                                  const Century& cen, uint64_t* cs, uint16_t* list, uint32_t lane) {
-    cs[lane * 3 + 0] = century_state(cen, K.s1);
-    cs[lane * 3 + 1] = century_state(cen, K.s2);
-    cs[lane * 3 + 2] = century_state(cen, K.sA);
-    const uint32_t cnt = __popcll(mb.lo) + __popcll(mb.hi);
-    uint32_t inc = cnt;
+__device__ __noinline__ void insert_slab_dense(const FilterK K, uint32_t* __restrict__ bits, Bits128 mb, const Century cen, uint32_t list_addr) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t C1 = century_state(cen, K.s1), C2 = century_state(cen, K.s2), CA = century_state(cen, K.sA);
+    uint64_t lo = mb.lo, hi = mb.hi;
+    uint32_t total;
+    do {                                                             // rounds of at most I2_CAP items (one round unless p > 16 % locally)
+        const uint32_t cnt = __popcll(lo) + __popcll(hi);
+        uint32_t inc = cnt;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= (uint32_t)d) inc += t;
-    }
-    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-    uint32_t off = inc - cnt;
-    uint64_t v = mb.lo;
-    while (v) { list[off++] = (uint16_t)((lane << 7) | (uint32_t)(__ffsll((long long)v) - 1)); v &= v - 1ull; }
-    v = mb.hi;
-    while (v) { list[off++] = (uint16_t)((lane << 7) | (uint32_t)(__ffsll((long long)v) + 63)); v &= v - 1ull; }
-    __syncwarp();
-    for (uint32_t base = 0; base < total; base += 32u) {
-        const uint32_t i = base + lane;
-        if (i < total) {
-            const uint32_t tag = list[i];
-            const uint32_t owner = tag >> 7, pos = tag & 127u, x = pos / 10u, y = pos - 10u * x;
-            const uint64_t h1 = finish_t<KIND>(decade_state_t<KIND>(cs[owner * 3 + 0], K.s1, x), K.s1, y);
-            const uint64_t h2 = finish_t<KIND>(decade_state_t<KIND>(cs[owner * 3 + 1], K.s2, x), K.s2, y);
-            uint32_t idx = mod_u64(h1, K.fm);
-            const uint32_t step = mod_u64(h2, K.fm);
-            for (uint32_t p = 0; p < K.fk; p++) {
-                red_or_global(bits + (idx >> 5), 1u << (idx & 31u));
-                idx = addmod(idx, step, K.fm.m);
-            }
-            if (K.has_act) {
-                const uint64_t hA = finish_t<KIND>(decade_state_t<KIND>(cs[owner * 3 + 2], K.sA, x), K.sA, y);
-                if (hA < K.T) red_or_global(bits + (idx >> 5), 1u << (idx & 31u));
-            }
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (uint32_t)d) inc += t;
         }
-    }
-    __syncwarp();
+        total = __shfl_sync(0xffffffffu, inc, 31);
+        uint32_t off = inc - cnt;
+        while (lo && off < (uint32_t)I2_CAP) {
+            const uint32_t b = (uint32_t)(__ffsll((long long)lo) - 1); lo &= lo - 1ull;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(list_addr + 2u * off), "h"((uint16_t)((lane << 7) | b)) : "memory");
+            off++;
+        }
+        while (hi && off < (uint32_t)I2_CAP) {
+            const uint32_t b = (uint32_t)(__ffsll((long long)hi) + 63); hi &= hi - 1ull;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(list_addr + 2u * off), "h"((uint16_t)((lane << 7) | b)) : "memory");
+            off++;
+        }
+        __syncwarp();
+        const uint32_t ntot = min(total, (uint32_t)I2_CAP);
+#pragma unroll 1
+        for (uint32_t base = 0; base < ntot; base += 32u) {
+            const uint32_t i = base + lane;
+            uint16_t t16;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(t16) : "r"(list_addr + 2u * min(i, (uint32_t)(I2_CAP - 1))) : "memory");
+            const bool have = i < ntot;
+            if (K.fk == 3u) insert_batch<KIND, 3>(K, bits, t16, have, C1, C2, CA);
+            else if (K.fk == 2u) insert_batch<KIND, 2>(K, bits, t16, have, C1, C2, CA);
+            else insert_batch<KIND, 0>(K, bits, t16, have, C1, C2, CA);
+        }
+        __syncwarp();
+    } while (total > (uint32_t)I2_CAP);
 }
 
 __global__ void __launch_bounds__(I2_WARPS * 32) k_insert2(const FrameJob* __restrict__ jobs) {
     const FrameJob& J = jobs[blockIdx.y];
     if (J.l == 0) return;
-    __shared__ uint64_t s_cs[I2_WARPS][32 * 3];
-    __shared__ uint16_t s_list[I2_WARPS][I2_LIST];
+    __shared__ __align__(16) uint16_t s_list[I2_WARPS][I2_CAP];
     const FilterK K = filter_consts(J);
     const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31u;   // warp-uniform for the compiler
+    const uint32_t list_addr = smem_u32(&s_list[warp][0]);
     const uint32_t ncent = (J.n + 99u) / 100u;
     const uint32_t nslab = (ncent + 31u) / 32u;
+    const bool fast = K.fm.fast != 0u;                               // 2 <= m <= 2^30: the specialised path
     for (uint32_t sl = blockIdx.x * I2_WARPS + warp; sl < nslab; sl += gridDim.x * I2_WARPS) {
         const uint32_t slab = sl * 32u, c = slab + lane;
         const bool active = c < ncent;
@@ -142,17 +167,17 @@ __global__ void __launch_bounds__(I2_WARPS * 32) k_insert2(const FrameJob* __res
         if (active) mb = load_bits100(J.mask, c, min(100u, J.n - 100u * c));
         if (!__any_sync(0xffffffffu, (mb.lo | mb.hi) != 0ull)) continue;
         const uint32_t last = min(slab + 31u, ncent - 1u);
-        const bool uniform = slab >= 1u && ndigits_u32(slab) == ndigits_u32(last);
+        const bool uniform = fast && slab >= 1u && ndigits_u32(slab) == ndigits_u32(last);
         if (uniform) {
             const Century cen = make_century(active ? c : slab);
             switch (cen.kind) {
-            case K_4B: insert_slab_dense<K_4B>(K, J.bits, mb, cen, s_cs[warp], s_list[warp], lane); break;
-            case K_8B: insert_slab_dense<K_8B>(K, J.bits, mb, cen, s_cs[warp], s_list[warp], lane); break;
-            case K_44: insert_slab_dense<K_44>(K, J.bits, mb, cen, s_cs[warp], s_list[warp], lane); break;
-            case K_88: insert_slab_dense<K_88>(K, J.bits, mb, cen, s_cs[warp], s_list[warp], lane); break;
-            default:   insert_slab_dense<K_BB>(K, J.bits, mb, cen, s_cs[warp], s_list[warp], lane); break;
+            case K_4B: insert_slab_dense<K_4B>(K, J.bits, mb, cen, list_addr); break;
+            case K_8B: insert_slab_dense<K_8B>(K, J.bits, mb, cen, list_addr); break;
+            case K_44: insert_slab_dense<K_44>(K, J.bits, mb, cen, list_addr); break;
+            case K_88: insert_slab_dense<K_88>(K, J.bits, mb, cen, list_addr); break;
+            default:   insert_slab_dense<K_BB>(K, J.bits, mb, cen, list_addr); break;
             }
-        } else if ((mb.lo | mb.hi) != 0ull) {             // century 0 or a digit-count boundary: per-lane form
+        } else if ((mb.lo | mb.hi) != 0ull) {             // century 0, a digit-count boundary or a huge filter: per-lane form
             const Century cen = make_century(c);
             const uint64_t C1 = century_state(cen, K.s1), C2 = century_state(cen, K.s2), CA = century_state(cen, K.sA);
             for (int half = 0; half < 2; half++) {
@@ -166,156 +191,6 @@ __global__ void __launch_bounds__(I2_WARPS * 32) k_insert2(const FrameJob* __res
                                   K.has_act ? finish(cen.kind, decade_state(cen, CA, K.sA, x), K.sA, y) : 0ull);
                 }
             }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// K2 (privatised, `insert_variant` 2, the default): the Bloom array of the frame is built in SHARED memory.
-// k_insert2 sends one RED.OR per probe to L2 -- 1.3 M per 4K frame, 75 % of the L2 atomic rate with the SMs waiting --
-// although all of a frame's probes land in one 238 KB array.  Here a persistent CTA takes a task = (frame, 1/S of its
-// centuries), clears its copy of the array in shared memory (as much as fits: ~90 % of a 4K array; the rest of the index
-// range goes to L2 as before), inserts its items with shared-memory atomics and finally ORs the non-zero WORDS of the
-// copy into the global array: ~60 K word-wide REDs per task instead of 1.3 M bit-wide ones per frame.
-// Item handling is the dense form of k_insert2 (compacted item list per slab of 32 centuries) with the owner's century
-// states fetched by shuffle, floor(k)-specialised straight-line probes and the one-IMAD remainder of the query kernels.
-// ------------------------------------------------------------------------------------------
-constexpr int I3_WARPS = 16, I3_THREADS = 32 * I3_WARPS;
-constexpr int I3_CAP = 512;                                           // list entries per warp and round (uint16 each)
-
-template <bool HYB>
-__device__ __forceinline__ void set_bit_hyb(uint32_t sb_addr, uint32_t sw, uint32_t* __restrict__ gbits, uint32_t idx) {
-    const uint32_t w = idx >> 5, v = 1u << (idx & 31u);
-    if (!HYB || w < sw) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(sb_addr + 4u * w), "r"(v) : "memory");
-    else red_or_global(gbits + w, v);
-}
-
-template <int KIND, int FKT, bool HYB>
-__device__ __forceinline__ void insert_batch3(const FilterK& K, uint32_t sb_addr, uint32_t sw, uint32_t* __restrict__ gbits,
-                                              uint32_t tag, bool have, uint64_t C1, uint64_t C2, uint64_t CA) {
-    const uint32_t owner = (tag >> 7) & 31u, pos = tag & 127u, x = (pos * 205u) >> 11, y = pos - 10u * x;   // pos < 128: /10 exact
-    const uint64_t C1o = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)C1, owner) | ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(C1 >> 32), owner) << 32);
-    const uint64_t C2o = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)C2, owner) | ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(C2 >> 32), owner) << 32);
-    uint64_t CAo = 0;
-    if (K.has_act) CAo = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)CA, owner) | ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(CA >> 32), owner) << 32);
-    if (!have) return;
-    uint32_t idx = mod_fast(finish_t<KIND>(decade_state_t<KIND>(C1o, K.s1, x), K.s1, y), K.fm, K.nm);
-    const uint32_t step = mod_fast(finish_t<KIND>(decade_state_t<KIND>(C2o, K.s2, x), K.s2, y), K.fm, K.nm);
-    if (FKT > 0) {
-#pragma unroll
-        for (int p = 0; p < FKT; p++) { set_bit_hyb<HYB>(sb_addr, sw, gbits, idx); idx = addmod_fast(idx, step, K.fm.m); }
-    } else {
-        for (uint32_t p = 0; p < K.fk; p++) { set_bit_hyb<HYB>(sb_addr, sw, gbits, idx); idx = addmod_fast(idx, step, K.fm.m); }
-    }
-    if (K.has_act && finish_t<KIND>(decade_state_t<KIND>(CAo, K.sA, x), K.sA, y) < K.T) set_bit_hyb<HYB>(sb_addr, sw, gbits, idx);
-}
-
-template <int KIND, bool HYB>
-__device__ __noinline__ void insert_slab3(const FilterK K, uint32_t sb_addr, uint32_t sw, uint32_t* __restrict__ gbits, Bits128 mb,
-                                          const Century cen, uint32_t list_addr) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t C1 = century_state(cen, K.s1), C2 = century_state(cen, K.s2), CA = century_state(cen, K.sA);
-    uint64_t lo = mb.lo, hi = mb.hi;
-    uint32_t total;
-    do {                                                             // rounds of at most I3_CAP items (one round unless p > 16 % locally)
-        const uint32_t cnt = __popcll(lo) + __popcll(hi);
-        uint32_t inc = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= (uint32_t)d) inc += t;
-        }
-        total = __shfl_sync(0xffffffffu, inc, 31);
-        uint32_t off = inc - cnt;
-        while (lo && off < (uint32_t)I3_CAP) {
-            const uint32_t b = (uint32_t)(__ffsll((long long)lo) - 1); lo &= lo - 1ull;
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(list_addr + 2u * off), "h"((uint16_t)((lane << 7) | b)) : "memory");
-            off++;
-        }
-        while (hi && off < (uint32_t)I3_CAP) {
-            const uint32_t b = (uint32_t)(__ffsll((long long)hi) + 63); hi &= hi - 1ull;
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(list_addr + 2u * off), "h"((uint16_t)((lane << 7) | b)) : "memory");
-            off++;
-        }
-        __syncwarp();
-        const uint32_t ntot = min(total, (uint32_t)I3_CAP);
-#pragma unroll 1
-        for (uint32_t base = 0; base < ntot; base += 32u) {
-            const uint32_t i = base + lane;
-            uint16_t t16;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(t16) : "r"(list_addr + 2u * min(i, (uint32_t)(I3_CAP - 1))) : "memory");
-            const bool have = i < ntot;
-            if (K.fk == 3u) insert_batch3<KIND, 3, HYB>(K, sb_addr, sw, gbits, t16, have, C1, C2, CA);
-            else if (K.fk == 2u) insert_batch3<KIND, 2, HYB>(K, sb_addr, sw, gbits, t16, have, C1, C2, CA);
-            else insert_batch3<KIND, 0, HYB>(K, sb_addr, sw, gbits, t16, have, C1, C2, CA);
-        }
-        __syncwarp();
-    } while (total > (uint32_t)I3_CAP);
-}
-
-// tasks_per_frame = S: task t covers centuries [ncent*s/S, ncent*(s+1)/S) of frame t / S
-__global__ void __launch_bounds__(I3_THREADS, 1) k_insert3(const FrameJob* __restrict__ jobs, int F, uint32_t S, uint32_t smem_words_cap) {
-    extern __shared__ __align__(16) uint32_t dyn3[];
-    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31u;   // warp-uniform for the compiler
-    const uint32_t list_addr = smem_u32(dyn3) + 2u * I3_CAP * warp;
-    uint32_t* sbits = dyn3 + (I3_WARPS * I3_CAP) / 2;
-    const uint32_t sb_addr = smem_u32(sbits);
-    const uint32_t ntasks = (uint32_t)F * S;
-    for (uint32_t task = blockIdx.x; task < ntasks; task += gridDim.x) {
-        const FrameJob& J = jobs[task / S];
-        if (J.l == 0) continue;                                      // raw passthrough: no filter
-        const uint32_t s = task % S;
-        const FilterK K = filter_consts(J);
-        const uint32_t ncent = (J.n + 99u) / 100u;
-        const uint32_t c0 = (uint32_t)(((uint64_t)ncent * s) / S), c1 = (uint32_t)(((uint64_t)ncent * (s + 1u)) / S);
-        const uint32_t nwords = (J.l + 31u) >> 5;
-        const bool fast = K.fm.fast != 0u;                           // 2 <= m <= 2^30: the specialised path
-        const uint32_t sw = fast ? min(nwords, smem_words_cap) : 0u;
-        const bool hyb = sw < nwords;
-        __syncthreads();                                             // the previous task's merge has read the copy
-        for (uint32_t i = threadIdx.x; i < ((sw + 3u) >> 2); i += I3_THREADS)
-            asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(sb_addr + 16u * i), "r"(0u) : "memory");
-        __syncthreads();
-        for (uint32_t slab = c0 + 32u * warp; slab < c1; slab += 32u * I3_WARPS) {
-            const uint32_t c = slab + lane;
-            const bool active = c < c1;
-            Bits128 mb; mb.lo = 0; mb.hi = 0;
-            if (active) mb = load_bits100(J.mask, c, min(100u, J.n - 100u * c));
-            if (!__any_sync(0xffffffffu, (mb.lo | mb.hi) != 0ull)) continue;
-            const uint32_t last = min(slab + 31u, c1 - 1u);
-            const bool uniform = fast && slab >= 1u && ndigits_u32(slab) == ndigits_u32(last);
-            if (uniform) {
-                const Century cen = make_century(active ? c : slab);
-#define RBF_INS3(KD) { if (hyb) insert_slab3<KD, true>(K, sb_addr, sw, J.bits, mb, cen, list_addr); else insert_slab3<KD, false>(K, sb_addr, sw, J.bits, mb, cen, list_addr); }
-                switch (cen.kind) {
-                case K_4B: RBF_INS3(K_4B) break;
-                case K_8B: RBF_INS3(K_8B) break;
-                case K_44: RBF_INS3(K_44) break;
-                case K_88: RBF_INS3(K_88) break;
-                default:   RBF_INS3(K_BB) break;
-                }
-#undef RBF_INS3
-            } else if ((mb.lo | mb.hi) != 0ull) {             // century 0, a digit-count boundary or a huge filter: per-lane form, straight to L2
-                const Century cen = make_century(c);
-                const uint64_t C1 = century_state(cen, K.s1), C2 = century_state(cen, K.s2), CA = century_state(cen, K.sA);
-                for (int half = 0; half < 2; half++) {
-                    uint64_t v = half ? mb.hi : mb.lo;
-                    while (v) {
-                        const uint32_t pos = (uint32_t)(__ffsll((long long)v) - 1) + 64u * half;
-                        v &= v - 1ull;
-                        const uint32_t x = pos / 10u, y = pos - 10u * x;
-                        insert_hashes(J.bits, K, finish(cen.kind, decade_state(cen, C1, K.s1, x), K.s1, y),
-                                      finish(cen.kind, decade_state(cen, C2, K.s2, x), K.s2, y),
-                                      K.has_act ? finish(cen.kind, decade_state(cen, CA, K.sA, x), K.sA, y) : 0ull);
-                    }
-                }
-            }
-        }
-        __syncthreads();                                             // every warp's shared-memory atomics have landed
-        for (uint32_t i = threadIdx.x; i < sw; i += I3_THREADS) {     // merge: one RED per non-zero word
-            uint32_t v;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sb_addr + 4u * i) : "memory");
-            if (v) red_or_global(J.bits + i, v);
         }
     }
 }

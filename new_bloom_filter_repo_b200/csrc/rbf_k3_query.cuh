@@ -1,4 +1,4 @@
-// rbf_k3_query.cuh -- K3: Bloom test of all n positions -> pass mask (ivc:245-253, ivc:116-138): per-lane, staged rings, dense A+B, decade tiles, 2-CTA cluster.  Included by rbf_kernels.cu inside namespace rbf.
+// rbf_k3_query.cuh -- K3: Bloom test of all n positions -> pass mask (ivc:245-253, ivc:116-138): per-lane, staged rings, decade tiles.  Included by rbf_kernels.cu inside namespace rbf.
 #pragma once
 
 // ------------------------------------------------------------------------------------------
@@ -159,8 +159,6 @@ __device__ __forceinline__ void red_or_shared_if(uint32_t addr, uint32_t v, bool
 // bit `idx` of the Bloom array.  PM (probe mode):
 //   0  the whole array is in this CTA's shared memory
 //   1  words [0, sm_words) in shared memory, the rest through L2 (read-only path)
-//   2  the array is split over the shared memories of a 2-CTA cluster (DSMEM): words [0, sm_words) live in
-//      rank 0 (cluster address sm_addr), the rest in rank 1 (sm_addr1 is pre-biased by -4*sm_words)
 template <int PM>
 __device__ __forceinline__ uint32_t probe_bit(uint32_t sm_addr, uint32_t sm_addr1, const uint32_t* __restrict__ gl,
                                               uint32_t sm_words, uint32_t idx) {
@@ -172,11 +170,6 @@ __device__ __forceinline__ uint32_t probe_bit(uint32_t sm_addr, uint32_t sm_addr
         asm("{\n .reg .pred q;\n setp.lt.u32 q, %1, %2;\n mov.u32 %0, 0;\n @q ld.shared.u32 %0, [%3];\n @!q ld.global.nc.u32 %0, [%4];\n}"
             : "=r"(word)
             : "r"(w), "r"(sm_words), "r"(sm_addr + 4u * w), "l"(gl + w));
-    } else if (PM == 2) {
-        asm("{\n .reg .pred q;\n .reg .u32 b;\n setp.lt.u32 q, %1, %2;\n selp.u32 b, %3, %4, q;\n mad.lo.u32 b, %1, 4, b;\n"
-            " ld.shared::cluster.u32 %0, [b];\n}"
-            : "=r"(word)
-            : "r"(w), "r"(sm_words), "r"(sm_addr), "r"(sm_addr1));
     } else {
         asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(sm_addr + 4u * w));
     }
@@ -313,119 +306,14 @@ __device__ __noinline__ void query_slab_staged(const FilterK K, uint32_t sm_addr
 }
 
 // ------------------------------------------------------------------------------------------
-// K3 (dense A+B): stage B's hash is computed speculatively for EVERY position next to stage A's
-// (two independent XXH64 chains per position -> ILP, and no A->B ring: at a ~50 % survival rate the
-// ring bookkeeping costs more issue slots than the wasted half of the h2 hashes).  Only the ~12 % of
-// positions that pass all deterministic probes are compacted into the stage-C ring.
-// ------------------------------------------------------------------------------------------
-template <int KIND, int FKT, int PM>
-__device__ __noinline__ void query_slab_dense(const FilterK K, uint32_t sm_addr, uint32_t sm_addr1,
-                                              const uint32_t* __restrict__ gl, uint32_t sm_words,
-                                              const uint32_t* __restrict__ mask, uint32_t n, uint32_t slab_c0,
-                                              uint32_t c_end, uint4* __restrict__ pass4, uint32_t qc_addr,
-                                              uint32_t pacc_addr) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t c = slab_c0 + lane;
-    const bool active = c < c_end;
-    const Century cen = make_century(active ? c : slab_c0);
-    const uint64_t C1 = century_state(cen, K.s1), C2 = century_state(cen, K.s2), CA = century_state(cen, K.sA);
-    const uint32_t nvalid = active ? min(100u, n - 100u * c) : 0u;
-    Bits128 mb; mb.lo = 0; mb.hi = 0;
-    if (active && mask != nullptr) mb = load_bits100(mask, c, nvalid);
-    uint64_t skip_lo = mb.lo, skip_hi = mb.hi;                       // known members and positions beyond n
-    if (nvalid < 64u) { skip_hi = ~0ull; skip_lo |= ~((1ull << nvalid) - 1ull); }
-    else skip_hi |= ~((1ull << (nvalid - 64u)) - 1ull);
-    const uint32_t lt = (1u << lane) - 1u;
-    uint32_t qc_head = 0, qc_cnt = 0;
-#pragma unroll 1
-    for (uint32_t x = 0; x <= 10u; x++) {                            // x == 10: drain what is left in ring C
-        const bool feeding = x < 10u;
-        uint64_t D1 = 0, D2 = 0;
-        uint32_t skip10 = 0x3ffu;
-        if (feeding) {
-            D1 = decade_state_t<KIND>(C1, K.s1, x);
-            D2 = decade_state_t<KIND>(C2, K.s2, x);
-            const uint32_t p0 = 10u * x;
-            const uint64_t sh = (p0 < 64u) ? ((skip_lo >> p0) | (p0 ? (skip_hi << (64u - p0)) : 0ull)) : (skip_hi >> (p0 - 64u));
-            skip10 = (uint32_t)sh & 0x3ffu;
-        }
-        const uint32_t tagx = (lane << 8) | (x << 4);
-#pragma unroll 1
-        for (uint32_t y = 0; y < 10u; y++) {
-            if (feeding) {                                           // ---- stages A + B, every position
-                const uint32_t idx0 = mod_fast(finish_t<KIND>(D1, K.s1, y), K.fm, K.nm);
-                const uint32_t stepm = mod_fast(finish_t<KIND>(D2, K.s2, y), K.fm, K.nm);
-                uint32_t ok = probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx0) & ~(skip10 >> y) & 1u;
-                uint32_t idx = idx0;
-                if (FKT > 0) {
-#pragma unroll
-                    for (int i = 1; i < FKT; i++) {
-                        idx = addmod_fast(idx, stepm, K.fm.m);
-                        ok &= probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx);
-                    }
-                } else {
-                    for (uint32_t i = 1; i < K.fk; i++) {
-                        idx = addmod_fast(idx, stepm, K.fm.m);
-                        ok &= probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx);
-                    }
-                }
-                if (K.has_act) {
-                    idx = addmod_fast(idx, stepm, K.fm.m);           // index of probe floor_k
-                    const uint32_t b2 = __ballot_sync(0xffffffffu, ok != 0u);
-                    sts64_if(qc_addr + 8u * ((qc_head + qc_cnt + __popc(b2 & lt)) & (Q2_RING - 1)), idx, tagx | y, ok != 0u);
-                    qc_cnt += __popc(b2);
-                } else {
-                    deliver_pass(pacc_addr, tagx | y, ok != 0u);
-                }
-            }
-            if (qc_cnt >= 32u || (!feeding && qc_cnt > 0u)) {        // ---- stage C: 32 survivors
-                __syncwarp();
-                const uint32_t nc = min(32u, qc_cnt);
-                const bool have = lane < nc;
-                const uint2 r = lds64(qc_addr + 8u * ((qc_head + lane) & (Q2_RING - 1)));
-                qc_head = (qc_head + nc) & (Q2_RING - 1);
-                qc_cnt -= nc;
-                const uint32_t tag = have ? r.y : 0u;
-                const uint32_t owner = tag >> 8;
-                const uint64_t CAo = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)CA, owner) |
-                                     ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(CA >> 32), owner) << 32);
-                const uint64_t hA = finish_t<KIND>(decade_state_t<KIND>(CAo, K.sA, (tag >> 4) & 15u), K.sA, tag & 15u);
-                const uint32_t pb = probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, have ? r.x : 0u);
-                deliver_pass(pacc_addr, tag, have && (!(hA < K.T) || pb != 0u));
-            }
-            if (!feeding && qc_cnt == 0u) break;
-        }
-    }
-    __syncwarp();
-    uint4 acc = lds128(pacc_addr + 16u * lane);
-    sts128_if(pacc_addr + 16u * lane, 0u, 0u, 0u, 0u, true);
-    if (active) {
-        acc.x |= (uint32_t)mb.lo; acc.y |= (uint32_t)(mb.lo >> 32); acc.z |= (uint32_t)mb.hi; acc.w |= (uint32_t)(mb.hi >> 32);
-        pass4[c] = acc;
-    }
-    __syncwarp();
-}
-
-// ------------------------------------------------------------------------------------------
 // K3 (decade tiles): compaction without a per-position ring push.  A warp evaluates stage A for a
-// whole decade -- ten positions per lane, y a compile-time constant, ten independent XXH64 chains
-// per lane (ILP) -- then ONE warp scan of the survivor counts places every survivor in a flat
-// per-decade buffer of 4-byte records {idx0:23, lane:5, y:4}.  Stage B consumes the buffer in dense
-// batches of 32 and fetches the owner's decade state of seed 2 with a shuffle (all records of the
-// buffer belong to the current decade).  Survivors of B go through the small stage-C ring as before.
-// Requires m <= 2^23 (4K and 8K frames); larger filters use the ring kernel.
+// whole decade (or half of one) -- TY positions per lane, y a compile-time constant, TY independent
+// XXH64 chains per lane (ILP) -- then ONE warp scan of the survivor counts places every survivor in a
+// flat per-warp buffer of 4-byte records {idx0, lane, y}.  Stage B consumes the buffer in dense batches
+// of 32 and fetches the owner's decade state of seed 2 with a shuffle.  Survivors of B go through the
+// small stage-C ring.  (Round 1 shipped this as k_query3 with one buffer per decade; the kernel below
+// is its successor, see the comment there.)
 // ------------------------------------------------------------------------------------------
-#ifndef RBF_Q3_WARPS
-#define RBF_Q3_WARPS 28
-#endif
-constexpr int Q3_WARPS = RBF_Q3_WARPS, Q3_THREADS = 32 * Q3_WARPS;
-#ifndef RBF_Q3_TY
-#define RBF_Q3_TY 10
-#endif
-constexpr int Q3_TY = RBF_Q3_TY;                                        // positions of a decade per lane and tile: 10 or 5
-constexpr int Q3_BUF = 32 * Q3_TY;                                       // survivors of one tile of a slab, worst case
-constexpr int Q3_WARP_WORDS = Q3_BUF + (Q2_RING * 8 + 32 * 16 + 128) / 4;   // decade buffer, C ring, pass accumulators, digit table
-
 __device__ __forceinline__ void sts32_if(uint32_t addr, uint32_t v, bool p) {
     asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.shared.u32 [%0], %1;\n}" ::"r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
 }
@@ -454,206 +342,17 @@ __device__ __forceinline__ void drain_c_ring(const FilterK& K, uint32_t sm_addr,
     deliver_pass(pacc_addr, tag, have && (!(hA < K.T) || pb != 0u));
 }
 
-#ifdef RBF_Q3_INLINE
-#define RBF_Q3_FN __forceinline__
-#else
-#define RBF_Q3_FN __noinline__
-#endif
-template <int KIND, int FKT, int PM>
-__device__ RBF_Q3_FN void query_slab_tiled(const FilterK K, uint32_t sm_addr, uint32_t sm_addr1,
-                                              const uint32_t* __restrict__ gl, uint32_t sm_words,
-                                              const uint32_t* __restrict__ mask, uint32_t n, uint32_t slab_c0,
-                                              uint32_t c_end, uint4* __restrict__ pass4, uint32_t buf_addr) {
-    const uint32_t qc_addr = buf_addr + 4u * Q3_BUF, pacc_addr = qc_addr + 8u * Q2_RING, rb_addr = pacc_addr + 512u;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t c = slab_c0 + lane;
-    const bool active = c < c_end;
-    const Century cen = make_century(active ? c : slab_c0);
-    const uint64_t C1 = century_state(cen, K.s1), C2 = century_state(cen, K.s2), CA = century_state(cen, K.sA);
-    const uint32_t nvalid = active ? min(100u, n - 100u * c) : 0u;
-    uint64_t skip_lo = 0, skip_hi = 0;                               // known members and positions beyond n need no hashing
-    if (active && mask != nullptr) { const Bits128 mb = load_bits100(mask, c, nvalid); skip_lo = mb.lo; skip_hi = mb.hi; }
-    if (nvalid < 64u) { skip_hi = ~0ull; skip_lo |= ~((1ull << nvalid) - 1ull); }
-    else skip_hi |= ~((1ull << (nvalid - 64u)) - 1ull);
-    if (lane < 10u) sts64_if(rb_addr + 8u * lane, (uint32_t)c_rot_digit[lane], (uint32_t)(c_rot_digit[lane] >> 32), true);
-    const uint32_t lt = (1u << lane) - 1u;
-    uint32_t qc_head = 0, qc_cnt = 0;
-#pragma unroll 1
-    for (uint32_t x = 0; x < 10u; x++) {
-        const uint64_t D1 = decade_prep<KIND>(decade_state_t<KIND>(C1, K.s1, x));
-        const uint64_t D2 = decade_prep<KIND>(decade_state_t<KIND>(C2, K.s2, x));
-        const uint32_t p0 = 10u * x;
-        const uint64_t sh = (p0 < 64u) ? ((skip_lo >> p0) | (p0 ? (skip_hi << (64u - p0)) : 0ull)) : (skip_hi >> (p0 - 64u));
-#pragma unroll
-        for (int h = 0; h < 10 / Q3_TY; h++) {
-        // ---- stage A: Q3_TY positions per lane, y compile-time
-        uint32_t idx0[Q3_TY];
-        uint32_t sv = 0;
-#pragma unroll
-        for (int yy = 0; yy < Q3_TY; yy++) {
-            const uint32_t y = (uint32_t)(h * Q3_TY + yy);
-            idx0[yy] = mod_fast(finish_prep<KIND>(D1, K.s1, y, rot_digit_const(y)), K.fm, K.nm);
-            sv |= probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx0[yy]) << yy;
-        }
-        sv &= ~(uint32_t)(sh >> (h * Q3_TY)) & ((1u << Q3_TY) - 1u);
-        // ---- one scan per tile places the survivors
-        const uint32_t cnt = __popc(sv);
-        uint32_t inc = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= (uint32_t)d) inc += t;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-        uint32_t off = buf_addr + 4u * (inc - cnt);
-        const uint32_t ltag = lane << 23;
-#pragma unroll
-        for (int yy = 0; yy < Q3_TY; yy++) {
-            const bool p = ((sv >> yy) & 1u) != 0u;
-            sts32_if(off, idx0[yy] | ltag | ((uint32_t)(h * Q3_TY + yy) << 28), p);
-            off += p ? 4u : 0u;
-        }
-        __syncwarp();
-        // ---- stage B: dense batches of 32 survivors of this decade
-#pragma unroll 1
-        for (uint32_t b = 0; b < total; b += 32u) {
-            const uint32_t g = b + lane;
-            const bool have = g < total;
-            const uint32_t rec = lds32(buf_addr + 4u * min(g, (uint32_t)(Q3_BUF - 1)));
-            const uint32_t owner = (rec >> 23) & 31u, y = have ? (rec >> 28) : 0u;
-            const uint64_t D2o = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)D2, owner) |
-                                 ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(D2 >> 32), owner) << 32);
-            uint64_t rb = 0;
-            if (kind_ends_in_byte<KIND>()) { const uint2 t = lds64(rb_addr + 8u * y); rb = (uint64_t)t.x | ((uint64_t)t.y << 32); }
-            const uint32_t stepm = have ? mod_fast(finish_prep<KIND>(D2o, K.s2, y, rb), K.fm, K.nm) : 0u;
-            uint32_t idx = have ? (rec & 0x7fffffu) : 0u;
-            uint32_t ok = have ? 1u : 0u;
-            if (FKT > 0) {
-#pragma unroll
-                for (int i = 1; i < FKT; i++) {
-                    idx = addmod_fast(idx, stepm, K.fm.m);
-                    ok &= probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx);
-                }
-            } else {
-                for (uint32_t i = 1; i < K.fk; i++) {
-                    idx = addmod_fast(idx, stepm, K.fm.m);
-                    ok &= probe_bit<PM>(sm_addr, sm_addr1, gl, sm_words, idx);
-                }
-            }
-            const uint32_t tag = (owner << 8) | (x << 4) | y;
-            if (K.has_act) {
-                idx = addmod_fast(idx, stepm, K.fm.m);               // index of probe floor_k
-                const uint32_t b2 = __ballot_sync(0xffffffffu, ok != 0u);
-                sts64_if(qc_addr + 8u * ((qc_head + qc_cnt + __popc(b2 & lt)) & (Q2_RING - 1)), idx, tag, ok != 0u);
-                qc_cnt += __popc(b2);
-                if (qc_cnt >= 32u) drain_c_ring<KIND, PM>(K, sm_addr, sm_addr1, gl, sm_words, qc_addr, pacc_addr, lane, CA, qc_head, qc_cnt);
-            } else {
-                deliver_pass(pacc_addr, tag, ok != 0u);
-            }
-        }
-        __syncwarp();                                                // the tile buffer is rewritten next
-        }
-    }
-#pragma unroll 1
-    while (qc_cnt) drain_c_ring<KIND, PM>(K, sm_addr, sm_addr1, gl, sm_words, qc_addr, pacc_addr, lane, CA, qc_head, qc_cnt);
-    __syncwarp();
-    uint4 acc = lds128(pacc_addr + 16u * lane);
-    sts128_if(pacc_addr + 16u * lane, 0u, 0u, 0u, 0u, true);
-    if (active) {
-        if (mask != nullptr) {                                       // known members pass (no false negatives)
-            const Bits128 mb = load_bits100(mask, c, nvalid);
-            acc.x |= (uint32_t)mb.lo; acc.y |= (uint32_t)(mb.lo >> 32); acc.z |= (uint32_t)mb.hi; acc.w |= (uint32_t)(mb.hi >> 32);
-        }
-        pass4[c] = acc;
-    }
-    __syncwarp();
-}
-
-template <int PM>
-__global__ void __launch_bounds__(Q3_THREADS, 1) k_query3(const FrameJob* __restrict__ jobs, const uint32_t* __restrict__ cent_prefix,
-                                                          int F, uint32_t smem_words_cap) {
-    extern __shared__ __align__(128) uint32_t dyn[];
-    __shared__ __align__(8) uint64_t bar;
-    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31u;   // warp-uniform for the compiler
-    const uint32_t buf = smem_u32(dyn + warp * Q3_WARP_WORDS);
-    const uint32_t pacc = buf + 4u * Q3_BUF + 8u * Q2_RING;
-    uint32_t* sbits = dyn + Q3_WARPS * Q3_WARP_WORDS;
-    const uint32_t sb_addr = smem_u32(sbits);
-    sts128_if(pacc + 16u * lane, 0u, 0u, 0u, 0u, true);
-    const uint32_t total = cent_prefix[F];
-    const uint32_t lo = (uint32_t)(((uint64_t)total * blockIdx.x) / gridDim.x);
-    const uint32_t hi = (uint32_t)(((uint64_t)total * (blockIdx.x + 1)) / gridDim.x);
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
-    __syncthreads();
-    if (lo >= hi) return;
-    int f = 0;
-    { int a = 0, b = F; while (a < b) { int m = (a + b) >> 1; if (cent_prefix[m + 1] > lo) b = m; else a = m + 1; } f = a; }
-    uint32_t parity = 0, g = lo;
-    while (g < hi) {
-        while (cent_prefix[f + 1] <= g) f++;
-        const FrameJob& J = jobs[f];
-        const uint32_t seg_end = min(hi, cent_prefix[f + 1]);
-        const uint32_t c_begin = g - cent_prefix[f], c_end = seg_end - cent_prefix[f];
-        const uint32_t nwords = (J.l + 31u) >> 5;
-        const uint32_t sw = min((nwords + 3u) & ~3u, smem_words_cap);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            fence_proxy_async();
-            mbar_expect_tx(&bar, sw * 4u);
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(J.bits);
-            uint8_t* dst = reinterpret_cast<uint8_t*>(sbits);
-            for (uint32_t off = 0; off < sw * 4u; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, sw * 4u - off), &bar);
-        }
-        mbar_wait(&bar, parity);
-        parity ^= 1u;
-        const FilterK K = filter_consts(J);
-        uint4* pass4 = reinterpret_cast<uint4*>(J.pass);
-        for (uint32_t slab = c_begin + 32u * warp; slab < c_end; slab += 32u * Q3_WARPS) {
-            const uint32_t last = min(slab + 31u, c_end - 1u);
-            const bool uniform = slab >= 1u && ndigits_u32(slab) == ndigits_u32(last) && K.fk >= 1u && K.fm.fast && K.fm.m <= (1u << 23);
-            if (uniform) {
-#define RBF_TILED(KD)                                                                                                                   \
-    if (K.fk == 3u) query_slab_tiled<KD, 3, PM>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, buf);                       \
-    else if (K.fk == 2u) query_slab_tiled<KD, 2, PM>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, buf);                  \
-    else query_slab_tiled<KD, 0, PM>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, buf);
-                switch (make_century(slab).kind) {
-                case K_4B: { RBF_TILED(K_4B) } break;
-                case K_8B: { RBF_TILED(K_8B) } break;
-                case K_44: { RBF_TILED(K_44) } break;
-                case K_88: { RBF_TILED(K_88) } break;
-                default:   { RBF_TILED(K_BB) } break;
-                }
-#undef RBF_TILED
-            } else {                                    // century 0, a digit-count boundary, floor_k == 0 or a huge filter
-                const uint32_t c = slab + lane;
-                if (c < c_end) {
-                    BitView bv; bv.sm = sbits; bv.gl = J.bits; bv.sm_words = sw;
-                    const Bits128 r = query_century(bv, K, c, min(100u, J.n - 100u * c));
-                    pass4[c] = make_uint4((uint32_t)r.lo, (uint32_t)(r.lo >> 32), (uint32_t)r.hi, (uint32_t)(r.hi >> 32));
-                }
-            }
-        }
-        g = seg_end;
-    }
-}
-
-template <int KIND, int PM, int ALG = 0>
+template <int KIND, int PM>
 __device__ __forceinline__ void query_slab_dispatch(const FilterK& K, uint32_t sm_addr, uint32_t sm_addr1, const uint32_t* __restrict__ gl,
                                                     uint32_t sm_words, const uint32_t* __restrict__ mask, uint32_t n,
                                                     uint32_t slab_c0, uint32_t c_end, uint4* __restrict__ pass4, uint32_t qb,
                                                     uint32_t qc, uint32_t pacc) {
-    if (ALG == 1) {                                       // dense A+B, ring only before stage C
-        if (K.fk == 3u) query_slab_dense<KIND, 3, PM>(K, sm_addr, sm_addr1, gl, sm_words, mask, n, slab_c0, c_end, pass4, qc, pacc);
-        else if (K.fk == 2u) query_slab_dense<KIND, 2, PM>(K, sm_addr, sm_addr1, gl, sm_words, mask, n, slab_c0, c_end, pass4, qc, pacc);
-        else query_slab_dense<KIND, 0, PM>(K, sm_addr, sm_addr1, gl, sm_words, mask, n, slab_c0, c_end, pass4, qc, pacc);
-    } else {
-        if (K.fk == 3u) query_slab_staged<KIND, 3, PM>(K, sm_addr, sm_addr1, gl, sm_words, mask, n, slab_c0, c_end, pass4, qb, qc, pacc);
-        else if (K.fk == 2u) query_slab_staged<KIND, 2, PM>(K, sm_addr, sm_addr1, gl, sm_words, mask, n, slab_c0, c_end, pass4, qb, qc, pacc);
-        else query_slab_staged<KIND, 0, PM>(K, sm_addr, sm_addr1, gl, sm_words, mask, n, slab_c0, c_end, pass4, qb, qc, pacc);
-    }
+    if (K.fk == 3u) query_slab_staged<KIND, 3, PM>(K, sm_addr, sm_addr1, gl, sm_words, mask, n, slab_c0, c_end, pass4, qb, qc, pacc);
+    else if (K.fk == 2u) query_slab_staged<KIND, 2, PM>(K, sm_addr, sm_addr1, gl, sm_words, mask, n, slab_c0, c_end, pass4, qb, qc, pacc);
+    else query_slab_staged<KIND, 0, PM>(K, sm_addr, sm_addr1, gl, sm_words, mask, n, slab_c0, c_end, pass4, qb, qc, pacc);
 }
 
-template <bool HYBRID, int ALG>
+template <bool HYBRID>
 __global__ void __launch_bounds__(Q2_THREADS, 1) k_query2(const FrameJob* __restrict__ jobs,
                                                           const uint32_t* __restrict__ cent_prefix, int F,
                                                           uint32_t smem_words_cap) {
@@ -698,11 +397,11 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_query2(const FrameJob* __rest
             const bool uniform = slab >= 1u && ndigits_u32(slab) == ndigits_u32(last) && K.fk >= 1u && K.fm.fast;
             if (uniform) {
                 switch (make_century(slab).kind) {
-                case K_4B: query_slab_dispatch<K_4B, (HYBRID ? 1 : 0), ALG>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                case K_8B: query_slab_dispatch<K_8B, (HYBRID ? 1 : 0), ALG>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                case K_44: query_slab_dispatch<K_44, (HYBRID ? 1 : 0), ALG>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                case K_88: query_slab_dispatch<K_88, (HYBRID ? 1 : 0), ALG>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                default:   query_slab_dispatch<K_BB, (HYBRID ? 1 : 0), ALG>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_4B: query_slab_dispatch<K_4B, (HYBRID ? 1 : 0)>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_8B: query_slab_dispatch<K_8B, (HYBRID ? 1 : 0)>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_44: query_slab_dispatch<K_44, (HYBRID ? 1 : 0)>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                case K_88: query_slab_dispatch<K_88, (HYBRID ? 1 : 0)>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
+                default:   query_slab_dispatch<K_BB, (HYBRID ? 1 : 0)>(K, sb_addr, 0u, J.bits, sw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
                 }
             } else {                                    // century 0, a digit-count boundary, or floor_k == 0
                 const uint32_t c = slab + lane;
@@ -715,89 +414,6 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_query2(const FrameJob* __rest
         }
         g = seg_end;
     }
-}
-
-// ------------------------------------------------------------------------------------------
-// K3 (cluster): the same staged query for Bloom arrays that do not fit one CTA's shared memory.
-// A cluster of two CTAs (two SMs) shares one frame: each CTA stages HALF of the bit array with TMA
-// into its own shared memory and probes the other half through distributed shared memory
-// (ld.shared::cluster), so no probe goes to L2.  The two CTAs interleave the slabs of the cluster's
-// century range; two cluster barriers per frame segment order the re-staging.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
-    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q2_THREADS, 1)
-k_query2c(const FrameJob* __restrict__ jobs, const uint32_t* __restrict__ cent_prefix, int F, uint32_t half_words_cap) {
-    extern __shared__ __align__(128) uint32_t dyn[];
-    __shared__ __align__(8) uint64_t bar;
-    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31u;   // warp-uniform for the compiler
-    const uint32_t rank = cluster_ctarank();
-    const uint32_t cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
-    uint32_t* wq = dyn + warp * Q2_WARP_WORDS;
-    const uint32_t qb = smem_u32(wq), qc = smem_u32(wq + Q2_RING * 4), pacc = smem_u32(wq + Q2_RING * 4 + Q2_RING * 2);
-    uint32_t* sbits = dyn + Q2_WARPS * Q2_WARP_WORDS;
-    const uint32_t base0 = mapa_shared(smem_u32(sbits), 0u), base1 = mapa_shared(smem_u32(sbits), 1u);
-    sts128_if(pacc + 16u * lane, 0u, 0u, 0u, 0u, true);
-    const uint32_t total = cent_prefix[F];
-    const uint32_t lo = (uint32_t)(((uint64_t)total * cid) / ncl);
-    const uint32_t hi = (uint32_t)(((uint64_t)total * (cid + 1)) / ncl);
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
-    __syncthreads();
-    int f = 0;
-    { int a = 0, b = F; while (a < b) { int m = (a + b) >> 1; if (cent_prefix[m + 1] > lo) b = m; else a = m + 1; } f = a; }
-    uint32_t parity = 0, g = lo;
-    while (g < hi) {                                                  // both CTAs of the cluster walk the same segments
-        while (cent_prefix[f + 1] <= g) f++;
-        const FrameJob& J = jobs[f];
-        const uint32_t seg_end = min(hi, cent_prefix[f + 1]);
-        const uint32_t c_begin = g - cent_prefix[f], c_end = seg_end - cent_prefix[f];
-        const uint32_t nwords = ((J.l + 31u) >> 5);
-        const uint32_t hw = min(((((nwords + 1u) >> 1) + 3u) & ~3u), half_words_cap);   // words held by rank 0
-        const uint32_t mine_begin = rank ? hw : 0u;
-        const uint32_t mine_words = rank ? ((nwords > hw ? nwords - hw : 0u) + 3u) & ~3u : hw;
-        cluster_sync_all();                                           // nobody still probes the previous array
-        if (threadIdx.x == 0) {
-            fence_proxy_async();
-            mbar_expect_tx(&bar, mine_words * 4u);
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(J.bits + mine_begin);
-            uint8_t* dst = reinterpret_cast<uint8_t*>(sbits);
-            for (uint32_t off = 0; off < mine_words * 4u; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, mine_words * 4u - off), &bar);
-        }
-        mbar_wait(&bar, parity);
-        parity ^= 1u;
-        cluster_sync_all();                                           // both halves are in place
-        const FilterK K = filter_consts(J);
-        uint4* pass4 = reinterpret_cast<uint4*>(J.pass);
-        const uint32_t a1 = base1 - 4u * hw;
-        for (uint32_t slab = c_begin + 32u * (warp + Q2_WARPS * rank); slab < c_end; slab += 64u * Q2_WARPS) {
-            const uint32_t last = min(slab + 31u, c_end - 1u);
-            const bool uniform = slab >= 1u && ndigits_u32(slab) == ndigits_u32(last) && K.fk >= 1u && K.fm.fast;
-            if (uniform) {
-                switch (make_century(slab).kind) {
-                case K_4B: query_slab_dispatch<K_4B, 2>(K, base0, a1, J.bits, hw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                case K_8B: query_slab_dispatch<K_8B, 2>(K, base0, a1, J.bits, hw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                case K_44: query_slab_dispatch<K_44, 2>(K, base0, a1, J.bits, hw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                case K_88: query_slab_dispatch<K_88, 2>(K, base0, a1, J.bits, hw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                default:   query_slab_dispatch<K_BB, 2>(K, base0, a1, J.bits, hw, J.mask, J.n, slab, c_end, pass4, qb, qc, pacc); break;
-                }
-            } else {                                    // rare slabs: probe the global copy
-                const uint32_t c = slab + lane;
-                if (c < c_end) {
-                    BitView bv; bv.sm = sbits; bv.gl = J.bits; bv.sm_words = 0u;
-                    const Bits128 r = query_century(bv, K, c, min(100u, J.n - 100u * c));
-                    pass4[c] = make_uint4((uint32_t)r.lo, (uint32_t)(r.lo >> 32), (uint32_t)r.hi, (uint32_t)(r.hi >> 32));
-                }
-            }
-        }
-        g = seg_end;
-    }
-    cluster_sync_all();                                               // a peer may still be reading this CTA's half
 }
 
 // ------------------------------------------------------------------------------------------

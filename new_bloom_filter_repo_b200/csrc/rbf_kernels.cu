@@ -171,29 +171,7 @@ cudaError_t launch_threshold(const PairJob* d_pairs, int F, uint32_t npix, int c
 
 cudaError_t launch_insert(const FrameJob* d_jobs, int F, uint32_t max_centuries, int variant, int sm_count, cudaStream_t st) {
     if (F <= 0 || max_centuries == 0) return cudaSuccess;
-    if (variant == 2) {                                   // bit array privatised in shared memory, word-wide merge
-        const int smem = query_max_smem_bytes();
-        cudaError_t e = cudaFuncSetAttribute(k_insert3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        // tasks per frame: the smallest split that fills the persistent grid evenly (<= 6 % idle in the last wave) without
-        // making tasks smaller than ~32 slabs per warp-round
-        const uint32_t nslab = (max_centuries + 31u) / 32u;
-        uint32_t S = 1, best = 1;
-        double best_waste = 1e9;
-        for (S = 1; S <= 16u; S++) {
-            if (S > 1u && nslab / S < (uint32_t)(4 * I3_WARPS)) break;
-            const uint64_t tasks = (uint64_t)F * S;
-            const uint64_t waves = (tasks + (uint64_t)sm_count - 1) / (uint64_t)sm_count;
-            const double waste = (double)(waves * (uint64_t)sm_count) / (double)tasks - 1.0 + 0.008 * S;  // each split re-clears and re-merges the copy
-            if (waste < best_waste) { best_waste = waste; best = S; }
-        }
-        S = best;
-        uint32_t grid = (uint32_t)sm_count;
-        if ((uint64_t)F * S < grid) grid = (uint32_t)((uint64_t)F * S);
-        k_insert3<<<grid, I3_THREADS, smem, st>>>(d_jobs, F, S, (uint32_t)((smem - I3_WARPS * I3_CAP * 2) / 4) & ~3u);
-        return cudaGetLastError();
-    }
-    if (variant == 1) {                                   // dense, warp-compacted insert
+    if (variant >= 1) {                                   // dense, warp-compacted insert
         const uint32_t nslab = (max_centuries + 31u) / 32u;
         uint32_t bx = (nslab + I2_WARPS - 1) / I2_WARPS;
         const uint32_t cap = (uint32_t)(sm_count * 12);
@@ -213,27 +191,30 @@ cudaError_t launch_insert(const FrameJob* d_jobs, int F, uint32_t max_centuries,
 
 int query_max_smem_bytes() { return 232448 - 1024; }    // 227 KB opt-in minus static shared memory + slack
 
-template <bool HYBRID, int ALG>
+template <bool HYBRID>
 static cudaError_t launch_query2_t(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, int F, uint32_t total_centuries,
                                    int sm_count, int smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(k_query2<HYBRID, ALG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_query2<HYBRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     uint32_t grid = (uint32_t)sm_count;
     const uint32_t max_useful = (total_centuries + Q2_THREADS - 1) / Q2_THREADS;
     if (grid > max_useful) grid = max_useful;
     if (grid < 1u) grid = 1u;
-    k_query2<HYBRID, ALG><<<grid, Q2_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F,
-                                                     (uint32_t)((smem - Q2_WARPS * Q2_WARP_WORDS * 4) / 4));
+    k_query2<HYBRID><<<grid, Q2_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F, (uint32_t)((smem - Q2_WARPS * Q2_WARP_WORDS * 4) / 4));
     return cudaGetLastError();
 }
 
+// variant: 0 per-lane kernel; 1 staged rings; 5 decade tiles (half-decade tiles for 2^23 < m <= 2^24, rings beyond); 6 half-decade
+// tiles for every m <= 2^24.  (Round 1's 2 = DSMEM cluster, 3 = dense A+B and 4 = tiles without the batch carry were measured
+// slower and removed; DESIGN.md keeps their numbers.  The values still select the current default.)
 cudaError_t launch_query(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, int F, uint32_t total_centuries,
                          uint32_t max_l_bits, int variant, int sm_count, int smem_bytes_cap, cudaStream_t st) {
     if (F <= 0 || total_centuries == 0) return cudaSuccess;
     int cap = smem_bytes_cap & ~15;
     if (cap > query_max_smem_bytes()) cap = query_max_smem_bytes() & ~15;
     const uint32_t need_words = (((max_l_bits + 31u) >> 5) + 3u) & ~3u;
-    if (variant >= 5 && max_l_bits <= (1u << 24)) {       // decade tiles, round 2 (full stage-B batches with carry)
+    if (variant >= 2 && variant <= 4) variant = 5;
+    if (variant >= 5 && max_l_bits <= (1u << 24)) {       // decade tiles (full stage-B batches with carry)
         const bool half = (variant == 6) || max_l_bits > (1u << 23);      // half-decade tiles: 24-bit record indices
         const int qbytes = 4 * (Q4_TABLE_WORDS + Q4_WARPS * (half ? Q4Cfg<5>::WARP_WORDS : Q4Cfg<10>::WARP_WORDS));
         if (cap < qbytes + 1024) cap = qbytes + 1024;
@@ -256,54 +237,14 @@ cudaError_t launch_query(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, 
 #undef RBF_LAUNCH_Q4
         return cudaGetLastError();
     }
-    if (variant >= 5) variant = 1;                        // m > 2^24: ring kernel
-    if (variant == 4 && max_l_bits <= (1u << 23)) {       // decade tiles (records carry 23-bit indices)
-        const int qbytes = Q3_WARPS * Q3_WARP_WORDS * 4;
-        if (cap < qbytes + 1024) cap = qbytes + 1024;
-        const int bits_cap = cap - qbytes;
-        const bool fits = (size_t)need_words * 4 <= (size_t)bits_cap;
-        const int smem = qbytes + (fits ? (int)(need_words * 4 < 16 ? 16 : need_words * 4) : bits_cap);
-        uint32_t grid = (uint32_t)sm_count;
-        const uint32_t max_useful = (total_centuries + Q3_THREADS - 1) / Q3_THREADS;
-        if (grid > max_useful) grid = max_useful;
-        if (grid < 1u) grid = 1u;
-        cudaError_t e;
-        if (fits) {
-            e = cudaFuncSetAttribute(k_query3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return e;
-            k_query3<0><<<grid, Q3_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F, (uint32_t)((smem - qbytes) / 4));
-        } else {
-            e = cudaFuncSetAttribute(k_query3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return e;
-            k_query3<1><<<grid, Q3_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F, (uint32_t)((smem - qbytes) / 4));
-        }
-        return cudaGetLastError();
-    }
-    if (variant >= 1) {                                   // staged, queue-compacted kernels
-        if (variant == 4) variant = 1;
+    if (variant >= 1) {                                   // staged rings (also the home of filters beyond 2^24 bits)
         const int qbytes = Q2_WARPS * Q2_WARP_WORDS * 4;
         if (cap < qbytes + 1024) cap = qbytes + 1024;
         const int bits_cap = cap - qbytes;
         const bool fits = (size_t)need_words * 4 <= (size_t)bits_cap;
-        const uint32_t half_words = ((((need_words + 1u) >> 1) + 3u) & ~3u) + 4u;
-        if (variant == 2 && !fits && (size_t)half_words * 4 <= (size_t)bits_cap && sm_count >= 2) {
-            // two-CTA clusters: each CTA holds half of the array, the other half is probed through DSMEM
-            const int smem = qbytes + (int)(half_words * 4);
-            cudaError_t e = cudaFuncSetAttribute(k_query2c, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return e;
-            uint32_t grid = (uint32_t)(sm_count & ~1);
-            const uint32_t max_useful = 2u * ((total_centuries + 2 * Q2_THREADS - 1) / (2 * Q2_THREADS));
-            if (grid > max_useful) grid = max_useful;
-            if (grid < 2u) grid = 2u;
-            k_query2c<<<grid, Q2_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F, (uint32_t)((smem - qbytes) / 4));
-            return cudaGetLastError();
-        }
         const int smem = qbytes + (fits ? (int)(need_words * 4 < 16 ? 16 : need_words * 4) : bits_cap);
-        if (variant == 3)
-            return !fits ? launch_query2_t<true, 1>(d_jobs, d_cent_prefix, F, total_centuries, sm_count, smem, st)
-                         : launch_query2_t<false, 1>(d_jobs, d_cent_prefix, F, total_centuries, sm_count, smem, st);
-        return !fits ? launch_query2_t<true, 0>(d_jobs, d_cent_prefix, F, total_centuries, sm_count, smem, st)
-                     : launch_query2_t<false, 0>(d_jobs, d_cent_prefix, F, total_centuries, sm_count, smem, st);
+        return !fits ? launch_query2_t<true>(d_jobs, d_cent_prefix, F, total_centuries, sm_count, smem, st)
+                     : launch_query2_t<false>(d_jobs, d_cent_prefix, F, total_centuries, sm_count, smem, st);
     }
     int smem = (size_t)need_words * 4 > (size_t)cap ? cap : (int)(need_words * 4);
     if (smem < 16) smem = 16;

@@ -34,7 +34,7 @@ def main():
     st.upload(frames)
     base = {"query_variant": 5, "insert_variant": 1, "encode_ranges": 1, "pipe_k1_ctas_per_sm": 4, "query_smem_bytes": 0}
     sweep = json.loads(args.configs) if args.configs else [
-        {}, {"query_variant": 4}, {"query_variant": 6}, {"insert_variant": 2}, {"encode_ranges": 4},
+        {}, {"query_variant": 1}, {"query_variant": 6}, {"insert_variant": 0}, {"encode_ranges": 4},
         {"query_smem_bytes": 200000}, {"query_smem_bytes": 170000}, {"query_smem_bytes": 140000}, {"query_smem_bytes": 110000},
     ]
     out = open(args.out, "w") if args.out else None

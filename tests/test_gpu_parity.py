@@ -135,13 +135,13 @@ def test_compress_vs_oracle_ragged_sizes(pkg, co, n, p_gen, seed):
     assert np.array_equal(dec, m)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [0, 1, 5, 6])
 @pytest.mark.parametrize("n,p_gen,seed", [(101, 0.1, 21), (99999, 0.12, 22), (2073600, 0.0499, 23), (8294400, 0.03, 24),
                                           (8294400, 0.19, 25), (33177600, 0.08, 26), (33177600, 0.2, 27)])
 def test_query_kernel_variants_vs_oracle(pkg, co, variant, n, p_gen, seed):
-    """Every K3 formulation (per-lane, staged rings, DSMEM cluster, dense A+B, decade tiles of round 1, decade / half-decade
-    tiles with carried batches) gives the oracle's bitmap and witness bit for bit; the last sizes have l > 2^23 (round-1 tiles
-    hand over to the rings, the round-2 kernel switches to half-decade tiles with 24-bit records) and l > 2^24 (rings)."""
+    """Every K3 formulation (per-lane, staged rings, decade / half-decade tiles with carried batches) gives the oracle's bitmap
+    and witness bit for bit; the last sizes have l > 2^23 (the tile kernel switches to half-decade tiles with 24-bit records)
+    and l > 2^24 (rings)."""
     L, ctx = pkg._cabi.lib(), pkg._cabi.ctx()
     m = mask_for({"n": n, "p_gen": p_gen, "seed": seed})
     ob, ow, op, on, oratio, ok, ol = co.compress(m)
@@ -157,7 +157,7 @@ def test_query_kernel_variants_vs_oracle(pkg, co, variant, n, p_gen, seed):
         L.rbf_set_option(ctx, b"query_variant", 5)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [0, 1, 5, 6])
 @pytest.mark.parametrize("k,l", [(3.5, 16), (2.2, 5), (3.0, 64), (1.0, 7), (2.999, 2), (3.4, 40000)])
 def test_query_saturated_filter_and_empty_regions(pkg, co, variant, k, l):
     """A tiny (saturated) Bloom array makes every position survive every stage -- the survivor buffers and the stage-C ring
@@ -179,14 +179,13 @@ def test_query_saturated_filter_and_empty_regions(pkg, co, variant, k, l):
         L.rbf_set_option(ctx, b"query_variant", 5)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("n,p_gen,seed,kl", [(101, 0.1, 31, None), (99999, 0.12, 32, None), (8294400, 0.05, 33, None), (8294400, 0.31, 34, None),
                                              (33177600, 0.05, 35, None), (150000, 0.3, 36, (3.5, 16)), (2073600, 0.05, 37, (2.0, 2 ** 20)),
                                              (640000, 0.0004, 38, None)])
 def test_insert_kernel_variants_vs_oracle(pkg, co, variant, n, p_gen, seed, kl):
-    """K2 per-lane (0), warp-compacted with one RED per probe (1) and privatised in shared memory with a word-wide merge (2):
-    the same bit array as the oracle -- arrays smaller and larger than the shared-memory copy, dense slabs that need several
-    list rounds (p = 0.31), power-of-two and saturated filters, nearly empty masks."""
+    """K2 per-lane (0) and warp-compacted (1): the same bit array as the oracle -- dense slabs that need several list rounds
+    (p = 0.31), power-of-two and saturated filters, nearly empty masks, 4K and 8K sizes."""
     L, ctx = pkg._cabi.lib(), pkg._cabi.ctx()
     m = mask_for({"n": n, "p_gen": p_gen, "seed": seed})
     ob, ow, op, on, oratio, ok, ol = co.compress(m, k_l_override=kl)
