@@ -53,8 +53,22 @@ def mix(kernel_pat, inner_pat=None):
         print("  %-10s %5d  %5.1f%%" % (op, c, 100.0 * c / max(1, len(body))))
 
 
+def census():
+    """Library-wide count of the mnemonics that show which hardware paths the kernels use."""
+    sass = subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True).stdout.splitlines()
+    pats = [("UBLKCP (cp.async.bulk: TMA bulk copy engine, 1-D)", r"\bUBLKCP"), ("UTMALDG / UTMASTG (tensor-map TMA)", r"\bUTMA(LDG|STG)"),
+            ("SYNCS (mbarrier)", r"\bSYNCS"), ("REDG (fire-and-forget global atomics)", r"\bREDG"), ("ATOMS (shared-memory atomics)", r"\bATOMS"),
+            ("LDG.E.256 (32-byte vector loads)", r"\bLDG\.E\.(ENL2\.)?256"), ("VABSDIFF4 (byte-SIMD |a-b|)", r"\bVABSDIFF4"),
+            ("SHFL", r"\bSHFL"), ("VOTE", r"\bVOTE"), ("IMAD.WIDE", r"\bIMAD\.WIDE"), ("HMMA/UTCMMA (tensor cores; expected 0)", r"\b(HMMA|UTC\w*MMA|QGMMA|HGMMA)")]
+    nk = sum(1 for l in sass if "Function :" in l)
+    print("\n%d kernels, sm_100a; mnemonic census over the whole library:" % nk)
+    for name, pat in pats:
+        print("  %-58s %6d" % (name, sum(1 for l in sass if re.search(pat, l))))
+
+
 if __name__ == "__main__":
     if len(sys.argv) == 1:
         usage_table()
+        census()
     else:
         mix(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)

@@ -324,7 +324,7 @@ def test_stream_8k_u16_k_sweep(pkg, co):
     ch = rng.random((4320, 7680)) < 0.05
     f1[ch] = (f1[ch].astype(np.int64) + 16384) % 65536
     frames = np.stack([f0, f1])
-    for ks in (1.5, 4.0):
+    for ks in (1.5, 3.5, 4.0):           # l(3.5) just below 2^23 (decade tiles), l(4.0) above (half-decade tiles, 24-bit records)
         _check_stream_vs_oracle(pkg, co, frames, 3.0, k_over=ks)
 
 
