@@ -58,7 +58,7 @@ def census():
     sass = subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True).stdout.splitlines()
     pats = [("UBLKCP (cp.async.bulk: TMA bulk copy engine, 1-D)", r"\bUBLKCP"), ("UTMALDG / UTMASTG (tensor-map TMA)", r"\bUTMA(LDG|STG)"),
             ("SYNCS (mbarrier)", r"\bSYNCS"), ("REDG (fire-and-forget global atomics)", r"\bREDG"), ("ATOMS (shared-memory atomics)", r"\bATOMS"),
-            ("LDG.E.256 (32-byte vector loads)", r"\bLDG\.E\.(ENL2\.)?256"), ("VABSDIFF4 (byte-SIMD |a-b|)", r"\bVABSDIFF4"),
+            ("LDG ... .256 (32-byte vector loads)", r"\bLDG\.E[A-Z0-9.]*\.256"), ("VABSDIFF4 (byte-SIMD |a-b|)", r"\bVABSDIFF4"),
             ("SHFL", r"\bSHFL"), ("VOTE", r"\bVOTE"), ("IMAD.WIDE", r"\bIMAD\.WIDE"), ("HMMA/UTCMMA (tensor cores; expected 0)", r"\b(HMMA|UTC\w*MMA|QGMMA|HGMMA)")]
     nk = sum(1 for l in sass if "Function :" in l)
     print("\n%d kernels, sm_100a; mnemonic census over the whole library:" % nk)
