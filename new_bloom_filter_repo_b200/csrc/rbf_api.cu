@@ -54,6 +54,8 @@ struct rbf_ctx {
     int k1_only = 0;        // stop after K1 (mask + counts): VideoFrameCompressor._calculate_frame_diff
     int mask_mode = 0;      // 0: |dY| > thr (ivc:808); 1: additionally any byte of the pixel differs
     int query_smem_cap = 0;
+    int query_warps = 0;    // warps per CTA of the tile query kernel (0 = its compiled maximum, 28)
+    int kq_ranges = 1;      // > 1: K2 of range r+1 runs beside K3 of range r (see stream_encode_pipelined)
     char err[512];
     int64_t launches = 0, h2d = 0, d2h = 0;
     std::vector<void*> scratch;
@@ -267,6 +269,8 @@ extern "C" int rbf_set_option(rbf_ctx* c, const char* key, int64_t v) {
     if (!strcmp(key, "host_chunk_frames")) { c->host_chunk_frames = (int)v; return RBF_OK; }
     if (!strcmp(key, "k1_only")) { c->k1_only = v ? 1 : 0; return RBF_OK; }        // default of streams created afterwards
     if (!strcmp(key, "mask_mode")) { c->mask_mode = v ? 1 : 0; return RBF_OK; }    // (per-stream: rbf_stream_set_option)
+    if (!strcmp(key, "query_warps")) { c->query_warps = (int)v; return RBF_OK; }
+    if (!strcmp(key, "kq_ranges")) { c->kq_ranges = (int)(v < 1 ? 1 : (v > 8 ? 8 : v)); return RBF_OK; }
     if (!strcmp(key, "encode_ranges")) { c->encode_ranges = (int)(v < 1 ? 1 : (v > 8 ? 8 : v)); return RBF_OK; }
     if (!strcmp(key, "k1_ctas_per_sm")) { c->k1_ctas_per_sm = (int)(v < 1 ? 1 : (v > 64 ? 64 : v)); return RBF_OK; }
     if (!strcmp(key, "pipe_k1_ctas_per_sm")) { c->pipe_k1_ctas_per_sm = (int)(v < 1 ? 1 : (v > 64 ? 64 : v)); return RBF_OK; }
@@ -500,7 +504,7 @@ extern "C" int rbf_compress_mask(rbf_ctx* c, const uint8_t* mask, uint64_t n, co
     CK(c, cudaMemsetAsync(d_bits, 0, bit_words_padded(l) * 4, c->st));
     CK(c, cudaMemsetAsync(d_wit, 0, mw * 4, c->st));
     LAUNCH(c, launch_insert(d_job, 1, ncent, c->insert_variant, c->sm_count, c->st));
-    LAUNCH(c, launch_query(d_job, d_prefix, 1, ncent, (uint32_t)l, c->query_variant, c->sm_count, c->query_smem_cap, c->st));
+    LAUNCH(c, launch_query(d_job, d_prefix, 1, ncent, (uint32_t)l, c->query_variant, c->sm_count, c->query_smem_cap, c->query_warps, c->st));
     LAUNCH(c, launch_witness(d_job, 1, ncent, c->sm_count, (uint32_t*)((uint8_t*)d_small + 1024), d_cnt + 1, c->st)); c->launches += 2;
     CK(c, cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, c->st)); c->d2h += 16;
     CK(c, cudaStreamSynchronize(c->st));
@@ -556,7 +560,7 @@ extern "C" int rbf_decompress_mask(rbf_ctx* c, const uint8_t* bitmap, uint64_t l
     uint32_t h_prefix[2] = {0, ncent};
     CK(c, cudaMemcpyAsync(d_job, &J, sizeof J, cudaMemcpyHostToDevice, c->st));
     CK(c, cudaMemcpyAsync(d_prefix, h_prefix, 8, cudaMemcpyHostToDevice, c->st));
-    LAUNCH(c, launch_query(d_job, d_prefix, 1, ncent, (uint32_t)l, c->query_variant, c->sm_count, c->query_smem_cap, c->st));
+    LAUNCH(c, launch_query(d_job, d_prefix, 1, ncent, (uint32_t)l, c->query_variant, c->sm_count, c->query_smem_cap, c->query_warps, c->st));
     LAUNCH(c, launch_expand(d_job, 1, ncent, c->sm_count, (uint32_t*)((uint8_t*)d_small + 1024), d_cnt, c->st)); c->launches += 1;
     LAUNCH(c, launch_unpack_bits((const uint32_t*)d_out, (uint8_t*)d_bytes, n, c->st));
     uint32_t h_cnt = 0;
@@ -632,14 +636,14 @@ extern "C" int rbf_stream_create(rbf_ctx* c, uint32_t H, uint32_t W, uint32_t C,
     dalloc((void**)&s->d_pass, s->pass_stride_w * 4 * max_pairs);
     dalloc((void**)&s->d_jobs, sizeof(FrameJob) * max_pairs);
     dalloc((void**)&s->d_pairs, sizeof(PairJob) * max_pairs);
-    dalloc((void**)&s->d_prefix, 4 * (2 * (size_t)max_pairs + 4));
+    dalloc((void**)&s->d_prefix, 4 * (3 * (size_t)max_pairs + 32));
     dalloc((void**)&s->d_ones, 4 * (size_t)max_pairs);
     dalloc((void**)&s->d_resid, 4 * (size_t)max_pairs);
     dalloc((void**)&s->d_wlen, 4 * (size_t)max_pairs);
     dalloc((void**)&s->d_chunkcnt, 4 * 32 * (size_t)max_pairs);
     halloc((void**)&s->h_jobs, sizeof(FrameJob) * max_pairs);
     halloc((void**)&s->h_pairs, sizeof(PairJob) * max_pairs);
-    halloc((void**)&s->h_prefix, 4 * (2 * (size_t)max_pairs + 4));
+    halloc((void**)&s->h_prefix, 4 * (3 * (size_t)max_pairs + 32));
     halloc((void**)&s->h_ones, 4 * (size_t)max_pairs);
     halloc((void**)&s->h_resid, 4 * (size_t)max_pairs);
     halloc((void**)&s->h_wlen, 4 * (size_t)max_pairs);
@@ -818,7 +822,7 @@ static int stream_encode_range(rbf_stream* s, uint32_t first, uint32_t count, ui
     LAUNCH(c, launch_insert(s->d_jobs + first, (int)count, ncent, c->insert_variant, c->sm_count, c->st));
     if (record_events) CK(c, cudaEventRecord(s->ev[3], c->st));
     LAUNCH(c, launch_query(s->d_jobs + first, s->d_prefix + pfx, (int)count, rt.total_cent, rt.max_l, c->query_variant, c->sm_count,
-                           c->query_smem_cap, c->st));
+                           c->query_smem_cap, c->query_warps, c->st));
     if (record_events) CK(c, cudaEventRecord(s->ev[4], c->st));
     s->wit_dirty_full = true;                            // until the witness lengths of this encode are known
     LAUNCH(c, launch_witness(s->d_jobs + first, (int)count, ncent, c->sm_count, s->d_chunkcnt + 32 * (size_t)first, s->d_wlen + first, c->st));
@@ -879,6 +883,13 @@ static int stream_encode_pipelined(rbf_stream* s, uint32_t pairs, const uint32_t
     RangeTotals all;
     uint32_t base_cent = 0;
     bool first_k2 = true;
+    // K2 || K3 mode (kq_ranges > 1, serial K1): K2 is bound by L2 atomics with the SMs mostly waiting, K3 by instruction issue with
+    // L2 idle; K2 of range q+1 is enqueued on the second stream and runs BESIDE K3 of range q (K3 is then launched with fewer
+    // warps and a little less shared memory -- options query_warps / query_smem_bytes -- so that one K2 CTA fits next to it).
+    uint32_t Q = (R == 1u && !s->k1_only) ? (uint32_t)c->kq_ranges : 1u;
+    if (Q > 8u) Q = 8u;
+    if (pairs < 8u * Q) Q = 1u;
+    const bool kq = Q > 1u;
     for (uint32_t r = 0; r < R; r++) {
         const uint32_t f = lo[r], cnt = lo[r + 1] - lo[r];
         CK(c, cudaEventSynchronize(c->ev_k1[r]));         // this range's counts are on the host
@@ -893,7 +904,7 @@ static int stream_encode_pipelined(rbf_stream* s, uint32_t pairs, const uint32_t
         if (first_k2) { if (int e = wait_pack(c)) return e; }
         if (int e = stream_clear_outputs(s, f, cnt, rt.max_l, c->st)) return e;
         if (first_k2) { CK(c, cudaEventRecord(s->ev[2], c->st)); first_k2 = false; }
-        LAUNCH(c, launch_insert(s->d_jobs + f, (int)cnt, ncent, c->insert_variant, c->sm_count, c->st));
+        if (!kq) LAUNCH(c, launch_insert(s->d_jobs + f, (int)cnt, ncent, c->insert_variant, c->sm_count, c->st));
     }
     all.total_cent = base_cent;
     s->last_max_l = all.max_l;
@@ -902,9 +913,35 @@ static int stream_encode_pipelined(rbf_stream* s, uint32_t pairs, const uint32_t
         return RBF_OK;
     }
     CK(c, cudaMemcpyAsync(s->d_prefix, s->h_prefix, 4 * ((size_t)pairs + 1), cudaMemcpyHostToDevice, c->st));
-    CK(c, cudaEventRecord(s->ev[3], c->st));
-    LAUNCH(c, launch_query(s->d_jobs, s->d_prefix, (int)pairs, all.total_cent, all.max_l, c->query_variant, c->sm_count,
-                           c->query_smem_cap, c->st));
+    if (kq) {
+        uint32_t qlo[9];
+        for (uint32_t q = 0; q <= Q; q++) qlo[q] = (uint32_t)(((uint64_t)pairs * q) / Q);
+        // per-range work lists for K3 (each starts at 0), behind the whole-encode list that decode_verify uses
+        uint32_t* hp2 = s->h_prefix + pairs + 1;
+        uint32_t off = 0, range_cent[8], range_off[8];
+        for (uint32_t q = 0; q < Q; q++) {
+            range_off[q] = off;
+            const uint32_t b0 = s->h_prefix[qlo[q]];
+            for (uint32_t i = qlo[q]; i <= qlo[q + 1]; i++) hp2[off++] = s->h_prefix[i] - b0;
+            range_cent[q] = s->h_prefix[qlo[q + 1]] - b0;
+        }
+        CK(c, cudaMemcpyAsync(s->d_prefix + pairs + 1, hp2, 4 * (size_t)off, cudaMemcpyHostToDevice, c->st));
+        CK(c, cudaEventRecord(c->ev_fork, c->st));            // jobs, prefix lists and cleared outputs are in place
+        CK(c, cudaStreamWaitEvent(c->st_k1, c->ev_fork, 0));
+        for (uint32_t q = 0; q < Q; q++) {
+            const uint32_t f = qlo[q], cnt = qlo[q + 1] - qlo[q];
+            LAUNCH(c, launch_insert(s->d_jobs + f, (int)cnt, ncent, c->insert_variant, c->sm_count, c->st_k1));
+            CK(c, cudaEventRecord(c->ev_k1[q], c->st_k1));
+            CK(c, cudaStreamWaitEvent(c->st, c->ev_k1[q], 0));
+            if (q == 0) CK(c, cudaEventRecord(s->ev[3], c->st));
+            LAUNCH(c, launch_query(s->d_jobs + f, s->d_prefix + pairs + 1 + range_off[q], (int)cnt, range_cent[q], all.max_l, c->query_variant,
+                                   c->sm_count, c->query_smem_cap, c->query_warps, c->st));
+        }
+    } else {
+        CK(c, cudaEventRecord(s->ev[3], c->st));
+        LAUNCH(c, launch_query(s->d_jobs, s->d_prefix, (int)pairs, all.total_cent, all.max_l, c->query_variant, c->sm_count,
+                               c->query_smem_cap, c->query_warps, c->st));
+    }
     CK(c, cudaEventRecord(s->ev[4], c->st));
     s->wit_dirty_full = true;
     LAUNCH(c, launch_witness(s->d_jobs, (int)pairs, ncent, c->sm_count, s->d_chunkcnt, s->d_wlen, c->st));
@@ -1080,7 +1117,7 @@ extern "C" int rbf_stream_decode_verify(rbf_stream* s, uint32_t pairs, uint64_t*
     }
     CK(c, cudaMemcpyAsync(s->d_jobs, s->h_jobs, sizeof(FrameJob) * pairs, cudaMemcpyHostToDevice, c->st));
     const uint32_t total_cent = s->h_prefix[pairs];
-    LAUNCH(c, launch_query(s->d_jobs, s->d_prefix, (int)pairs, total_cent, s->last_max_l, c->query_variant, c->sm_count, c->query_smem_cap, c->st));
+    LAUNCH(c, launch_query(s->d_jobs, s->d_prefix, (int)pairs, total_cent, s->last_max_l, c->query_variant, c->sm_count, c->query_smem_cap, c->query_warps, c->st));
     LAUNCH(c, launch_expand(s->d_jobs, (int)pairs, (uint32_t)((s->npix + 99) / 100), c->sm_count, s->d_chunkcnt, s->d_wlen, c->st));
     c->launches += 1;
     void* d_cnt; int rc;

@@ -584,7 +584,8 @@ __global__ void __launch_bounds__(Q4_THREADS, 1) k_query4(const FrameJob* __rest
     const uint32_t rb_addr = smem_u32(dyn);                                    // digit constants, one table per CTA
     const uint32_t buf = smem_u32(dyn + Q4_TABLE_WORDS + warp * Cfg::WARP_WORDS);
     const uint32_t pacc = buf + 4u * Cfg::BUF + 8u * Q2_RING;
-    uint32_t* sbits = dyn + Q4_TABLE_WORDS + Q4_WARPS * Cfg::WARP_WORDS;
+    const uint32_t nwarps = blockDim.x >> 5;                                   // <= Q4_WARPS (register budget); fewer when K2 runs beside
+    uint32_t* sbits = dyn + Q4_TABLE_WORDS + nwarps * Cfg::WARP_WORDS;
     const uint32_t sb_addr = smem_u32(sbits);
     sts128_if(pacc + 16u * lane, 0u, 0u, 0u, 0u, true);
     if (threadIdx.x < 16u) {
@@ -619,7 +620,7 @@ __global__ void __launch_bounds__(Q4_THREADS, 1) k_query4(const FrameJob* __rest
         parity ^= 1u;
         const FilterK K = filter_consts(J);
         uint4* pass4 = reinterpret_cast<uint4*>(J.pass);
-        for (uint32_t slab = c_begin + 32u * warp; slab < c_end; slab += 32u * Q4_WARPS) {
+        for (uint32_t slab = c_begin + 32u * warp; slab < c_end; slab += 32u * nwarps) {
             const uint32_t last = min(slab + 31u, c_end - 1u);
             const bool uniform = slab >= 1u && ndigits_u32(slab) == ndigits_u32(last) && K.fk >= 1u && K.fm.fast && K.fm.m <= (1u << Cfg::IDXB);
             if (uniform) {

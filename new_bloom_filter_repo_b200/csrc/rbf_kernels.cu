@@ -208,21 +208,22 @@ static cudaError_t launch_query2_t(const FrameJob* d_jobs, const uint32_t* d_cen
 // tiles for every m <= 2^24.  (Round 1's 2 = DSMEM cluster, 3 = dense A+B and 4 = tiles without the batch carry were measured
 // slower and removed; DESIGN.md keeps their numbers.  The values still select the current default.)
 cudaError_t launch_query(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, int F, uint32_t total_centuries,
-                         uint32_t max_l_bits, int variant, int sm_count, int smem_bytes_cap, cudaStream_t st) {
+                         uint32_t max_l_bits, int variant, int sm_count, int smem_bytes_cap, int tile_warps, cudaStream_t st) {
     if (F <= 0 || total_centuries == 0) return cudaSuccess;
+    if (tile_warps < 4 || tile_warps > Q4_WARPS) tile_warps = Q4_WARPS;
     int cap = smem_bytes_cap & ~15;
     if (cap > query_max_smem_bytes()) cap = query_max_smem_bytes() & ~15;
     const uint32_t need_words = (((max_l_bits + 31u) >> 5) + 3u) & ~3u;
     if (variant >= 2 && variant <= 4) variant = 5;
     if (variant >= 5 && max_l_bits <= (1u << 24)) {       // decade tiles (full stage-B batches with carry)
         const bool half = (variant == 6) || max_l_bits > (1u << 23);      // half-decade tiles: 24-bit record indices
-        const int qbytes = 4 * (Q4_TABLE_WORDS + Q4_WARPS * (half ? Q4Cfg<5>::WARP_WORDS : Q4Cfg<10>::WARP_WORDS));
+        const int qbytes = 4 * (Q4_TABLE_WORDS + tile_warps * (half ? Q4Cfg<5>::WARP_WORDS : Q4Cfg<10>::WARP_WORDS));
         if (cap < qbytes + 1024) cap = qbytes + 1024;
         const int bits_cap = cap - qbytes;
         const bool fits = (size_t)need_words * 4 <= (size_t)bits_cap;
         const int smem = qbytes + (fits ? (int)(need_words * 4 < 16 ? 16 : need_words * 4) : bits_cap);
         uint32_t grid = (uint32_t)sm_count;
-        const uint32_t max_useful = (total_centuries + Q4_THREADS - 1) / Q4_THREADS;
+        const uint32_t max_useful = (total_centuries + 32u * tile_warps - 1) / (32u * tile_warps);
         if (grid > max_useful) grid = max_useful;
         if (grid < 1u) grid = 1u;
         const uint32_t words_cap = (uint32_t)((smem - qbytes) / 4);
@@ -230,7 +231,7 @@ cudaError_t launch_query(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, 
     do {                                                                                                              \
         cudaError_t e = cudaFuncSetAttribute(k_query4<PM, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);    \
         if (e != cudaSuccess) return e;                                                                               \
-        k_query4<PM, TY><<<grid, Q4_THREADS, smem, st>>>(d_jobs, d_cent_prefix, F, words_cap);                        \
+        k_query4<PM, TY><<<grid, 32 * tile_warps, smem, st>>>(d_jobs, d_cent_prefix, F, words_cap);                        \
     } while (0)
         if (fits) { if (half) RBF_LAUNCH_Q4(0, 5); else RBF_LAUNCH_Q4(0, 10); }
         else      { if (half) RBF_LAUNCH_Q4(1, 5); else RBF_LAUNCH_Q4(1, 10); }

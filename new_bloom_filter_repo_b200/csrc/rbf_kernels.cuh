@@ -52,7 +52,7 @@ cudaError_t launch_threshold(const PairJob* d_pairs, int F, uint32_t npix, int c
                              int sm_count, int ctas_per_sm, cudaStream_t st);
 cudaError_t launch_insert(const FrameJob* d_jobs, int F, uint32_t max_centuries, int variant, int sm_count, cudaStream_t st);
 cudaError_t launch_query(const FrameJob* d_jobs, const uint32_t* d_cent_prefix, int F, uint32_t total_centuries,
-                         uint32_t max_l_bits, int variant, int sm_count, int smem_bytes_cap, cudaStream_t st);
+                         uint32_t max_l_bits, int variant, int sm_count, int smem_bytes_cap, int tile_warps, cudaStream_t st);
 cudaError_t launch_witness(const FrameJob* d_jobs, int F, uint32_t max_centuries, int sm_count, uint32_t* d_scratch, uint32_t* d_wlen,
                            cudaStream_t st);
 cudaError_t launch_expand(const FrameJob* d_jobs, int F, uint32_t max_centuries, int sm_count, uint32_t* d_scratch, uint32_t* d_consumed,

@@ -814,3 +814,30 @@ def test_single_channel_frames_mask_gather_apply(pkg, dtype):
     assert np.array_equal(mask, om) and changed.dtype == dtype
     assert np.array_equal(changed, curr[np.where(om == 1)])
     assert np.array_equal(vfc._apply_frame_diff(prev, mask, changed), curr)
+
+
+def test_k2_beside_k3_matches_serial(pkg):
+    """kq_ranges > 1 runs K2 of range q+1 on a second stream beside K3 of range q (K3 with fewer warps / less shared memory so that
+    a K2 CTA fits next to it): same bytes as the serial encode, round trip intact."""
+    L, ctx = pkg._cabi.lib(), pkg._cabi.ctx()
+    frames = synth_stream(540, 960, 40, 19, [0.05, 0.02, 0.12, 0.0, 0.30, 0.40])
+    outs = {}
+    for name, opts in (("serial", {"kq_ranges": 1, "query_warps": 0, "query_smem_bytes": 0}),
+                       ("beside", {"kq_ranges": 4, "query_warps": 24, "query_smem_bytes": 222000}),
+                       ("beside8", {"kq_ranges": 8, "query_warps": 20, "query_smem_bytes": 200000})):
+        for k, v in opts.items():
+            pkg._cabi.check(L.rbf_set_option(ctx, k.encode(), v), ctx)
+        try:
+            st = pkg.FrameStream(540, 960, 3, np.uint8, max_frames=40)
+            st.upload(frames)
+            for _ in range(2):                                  # twice: the second call sees the first one's leftovers
+                res = st.encode_consecutive(40, 3.0)
+            assert not st.decode_verify().any()
+            bms, wts, _ = st.fetch_batch(0, 39)
+            outs[name] = [(r.ones, r.l, r.wlen, r.raw, bms[t].tobytes(), wts[t].tobytes()) for t, r in enumerate(res)]
+            st.close()
+        finally:
+            for k, v in (("kq_ranges", 1), ("query_warps", 0), ("query_smem_bytes", 0)):
+                L.rbf_set_option(ctx, k.encode(), v)
+    assert outs["serial"] == outs["beside"] == outs["beside8"]
+    assert any(o[3] for o in outs["serial"]) and not all(o[3] for o in outs["serial"])
