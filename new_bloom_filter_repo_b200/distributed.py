@@ -106,38 +106,66 @@ class PeerGather:
     kernel writing over NVLink.  Layout of `recv`: [half 0|1][rank][pair][slot_bytes]; `result()` returns the half that
     holds the last exchange as uint8[world, pairs, slot]."""
 
-    def __init__(self, dist, pairs: int, slot_bytes: int):
+    def __init__(self, dist, pairs: int, slot_bytes: int, _final_barrier: bool = True):
         L, ctx = _cabi.lib(), _cabi.ctx()
         self.world = dist.get_world_size() if dist is not None else 1
         self.rank = dist.get_rank() if dist is not None else 0
         self.pairs, self.slot = int(pairs), int(slot_bytes)
-        self.recv = DeviceBuffer(2 * self.world * self.pairs * self.slot)
-        self.flags = DeviceBuffer(256)
-        _cabi.check(L.rbf_memset(ctx, self.flags.ptr, 0, 256), ctx)
-        _cabi.check(L.rbf_sync(ctx), ctx)
-        mine = np.zeros((2, 64), dtype=np.uint8)
+        self.recv = self.flags = None
         self._opened = []
         recv_ptrs, flag_ptrs = (C.c_void_p * self.world)(), (C.c_void_p * self.world)()
+        mine = np.zeros((2, 64), dtype=np.uint8)
+        exported = None
+        try:                                              # allocation + export may fail on one rank only: the handle gather below
+            self.recv = DeviceBuffer(2 * self.world * self.pairs * self.slot)    # is entered by every rank regardless
+            self.flags = DeviceBuffer(256)
+            _cabi.check(L.rbf_memset(ctx, self.flags.ptr, 0, 256), ctx)
+            _cabi.check(L.rbf_sync(ctx), ctx)
+            if self.world > 1:
+                _cabi.check(L.rbf_peer_export(ctx, self.recv.ptr, _cabi.ptr(mine[0])), ctx)
+                _cabi.check(L.rbf_peer_export(ctx, self.flags.ptr, _cabi.ptr(mine[1])), ctx)
+            exported = mine.tobytes()
+        except _cabi.RbfError:
+            if self.world == 1:
+                raise
         if self.world > 1:
-            _cabi.check(L.rbf_peer_export(ctx, self.recv.ptr, _cabi.ptr(mine[0])), ctx)
-            _cabi.check(L.rbf_peer_export(ctx, self.flags.ptr, _cabi.ptr(mine[1])), ctx)
             handles = [None] * self.world
-            dist.all_gather_object(handles, mine.tobytes())
-            for r in range(self.world):
+            dist.all_gather_object(handles, exported)
+            if any(h is None for h in handles):
+                raise _cabi.RbfError("peer exchange: CUDA IPC export failed on rank(s) %s" % [r for r, h in enumerate(handles) if h is None])
+            for r in range(self.world):                   # no collectives below: a failure here is reported through try_create
                 if r == self.rank:
                     recv_ptrs[r], flag_ptrs[r] = self.recv.ptr.value, self.flags.ptr.value
                     continue
                 h = np.frombuffer(handles[r], dtype=np.uint8).reshape(2, 64).copy()
                 pr, pf = C.c_void_p(), C.c_void_p()
                 _cabi.check(L.rbf_peer_open(ctx, _cabi.ptr(h[0]), C.byref(pr)), ctx)
+                self._opened.append(pr)
                 _cabi.check(L.rbf_peer_open(ctx, _cabi.ptr(h[1]), C.byref(pf)), ctx)
-                self._opened += [pr, pf]
+                self._opened.append(pf)
                 recv_ptrs[r], flag_ptrs[r] = pr.value, pf.value
         else:
             recv_ptrs[0], flag_ptrs[0] = self.recv.ptr.value, self.flags.ptr.value
         _cabi.check(L.rbf_peer_gather_init(ctx, self.rank, self.world, recv_ptrs, flag_ptrs), ctx)
-        if dist is not None:
+        if dist is not None and _final_barrier:
             dist.barrier()                                  # nobody pushes before every rank has mapped and zeroed
+
+    @classmethod
+    def try_create(cls, dist, pairs: int, slot_bytes: int):
+        """PeerGather, or None on EVERY rank when CUDA IPC / peer access is unavailable on any rank (the caller then uses NCCL)."""
+        obj, ok = None, True
+        try:
+            obj = cls(dist, pairs, slot_bytes, _final_barrier=False)
+        except _cabi.RbfError:
+            ok = False
+        flags = [None] * dist.get_world_size()
+        dist.all_gather_object(flags, ok)
+        if all(flags):
+            dist.barrier()
+            return obj
+        if obj is not None:
+            obj.close(None)
+        return None
 
     def exchange(self, stream) -> None:
         """Enqueue the push of the last encode's bit arrays (overlaps the next encode; complete after rbf_sync)."""
@@ -158,7 +186,9 @@ class PeerGather:
         for p in self._opened:
             L.rbf_peer_close(ctx, p)
         self._opened = []
-        self.recv.free(); self.flags.free()
+        for b in (self.recv, self.flags):
+            if b is not None:
+                b.free()
 
 
 class ShardedStreamEncoder:
@@ -167,7 +197,7 @@ class ShardedStreamEncoder:
     on the block and exchanges the packed bit arrays with ONE all-gather, after which every rank holds the bit array of every
     pair of the stream.  The per-pair headers (l, |w|, p, k, ones, raw) travel as a small object gather next to it."""
 
-    def __init__(self, dist, height: int, width: int, channels: int, dtype, total_frames: int, gather: str = "nccl"):
+    def __init__(self, dist, height: int, width: int, channels: int, dtype, total_frames: int, gather: str = "p2p"):
         from .stream import FrameStream
         self.dist = dist
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
@@ -199,8 +229,10 @@ class ShardedStreamEncoder:
         self.slot = need
         n = self.layout["slots"]
         if self.gather == "p2p":
-            self._peer = PeerGather(self.dist, n, self.slot)
-        else:
+            self._peer = PeerGather.try_create(self.dist, n, self.slot)
+            if self._peer is None:
+                self.gather = "nccl (p2p unavailable: CUDA IPC failed on some rank)"
+        if self._peer is None:
             if not self._nccl_ready:
                 init_nccl_from_torch(self.dist)
                 self._nccl_ready = True

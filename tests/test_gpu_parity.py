@@ -841,3 +841,28 @@ def test_k2_beside_k3_matches_serial(pkg):
                 L.rbf_set_option(ctx, k.encode(), v)
     assert outs["serial"] == outs["beside"] == outs["beside8"]
     assert any(o[3] for o in outs["serial"]) and not all(o[3] for o in outs["serial"])
+
+
+def test_two_ranks_p2p_equals_nccl(pkg, tmp_path):
+    """One stream block-partitioned over 2 GPUs (ShardedStreamEncoder): the NCCL all-gather and the peer-memory push leave the same
+    bytes on both ranks, equal to a single-GPU encode of the whole stream.  Skipped on a 1-GPU box (bench.py --gpus N verifies the
+    same thing at N = 2 / 4 / 8 after its timed region: `gather_verified`, `strong_matches_single_gpu`)."""
+    import json
+    import socket
+    import subprocess
+    import sys
+    try:
+        ngpu = int(subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.count("GPU "))
+    except Exception:
+        ngpu = 1
+    if ngpu < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tests", "_rank_worker_gpu.py"), str(tmp_path)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    outs = [json.load(open(tmp_path / ("rank%d.json" % r))) for r in range(2)]
+    assert outs[0]["nccl"]["sha"] == outs[1]["nccl"]["sha"] == outs[0]["p2p"]["sha"] == outs[1]["p2p"]["sha"] == outs[0]["single_gpu_sha"]
+    assert outs[0]["p2p"]["l"] == outs[0]["single_gpu_l"] and outs[0]["p2p"]["used"] == "p2p"
