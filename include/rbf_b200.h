@@ -213,9 +213,12 @@ int rbf_nccl_destroy(rbf_ctx* ctx);
  *   receive buffer: 2 halves x nranks x pairs x slot_bytes (cudaMalloc via rbf_malloc); exchange number q lands in
  *   half q & 1 (rbf_peer_gather_half), so a rank may still read exchange q-1 while its peers deliver q;
  *   flag array: nranks uint32, zeroed by its owner before the handles are exchanged.
- * All ranks must use the same pairs and slot_bytes.  As with the NCCL form the call only enqueues work; the other
- * ranks' slots are complete after rbf_sync / rbf_timer_stop_ms / rbf_memcpy_d2h, which return an error if a peer
- * did not deliver within ~3 s instead of hanging. */
+ * All ranks must use the same pairs and slot_bytes (a multiple of 16).  As with the NCCL form the call only enqueues work; the
+ * other ranks' slots are complete after rbf_sync / rbf_timer_stop_ms / rbf_memcpy_d2h, which return an error if a peer
+ * did not deliver within ~3 s instead of hanging.
+ * CONTRACT: a rank must have finished reading exchange q-1 (copied it out, or consumed it on the context's stream) before it
+ * calls exchange q+1 -- exchange q+1 reuses the half that held q-1; the library only guarantees that no rank overwrites a half
+ * before every rank has signalled the exchange in between.  Validated at 2 and 8 GPUs (profiles/r02_n{2,8}_*_p2p.json). */
 int rbf_peer_export(rbf_ctx* ctx, const void* d_ptr, uint8_t handle_out[64]);
 int rbf_peer_open(rbf_ctx* ctx, const uint8_t handle[64], void** d_ptr_out);
 int rbf_peer_close(rbf_ctx* ctx, void* d_ptr);
