@@ -31,7 +31,13 @@ def run(h, w, nfr, threads, mode):
 
 
 if __name__ == "__main__":
-    for (h, w) in ((1080, 1920), (2160, 3840)):
+    import faulthandler
+    faulthandler.dump_traceback_later(120, repeat=True)          # a stuck run shows where
+    sizes = ((1080, 1920), (2160, 3840)) if "--4k" in sys.argv else ((1080, 1920),)
+    for (h, w) in sizes:
         for threads in (1, None):
             for mode in ("lossless", "reference"):
-                print(json.dumps(run(h, w, 30, threads, mode)), flush=True)
+                t0 = time.perf_counter()
+                line = run(h, w, 30, threads, mode)
+                line["wall_s_incl_synthesis_and_warmup"] = time.perf_counter() - t0
+                print(json.dumps(line), flush=True)

@@ -19,7 +19,11 @@ for r in rows[2:]:
 src = subprocess.run(["ncu","-i",rep,"--page","source","--csv","--kernel-name","regex:"+kern],capture_output=True,text=True).stdout
 rows=list(csv.reader(src.splitlines()))
 hi=[i for i,r in enumerate(rows) if r and r[0]=='Address'][0]
-hdr=rows[hi]; data=[r for r in rows[hi+1:] if len(r)==len(hdr) and r[0]!='Address']
+hdr=rows[hi]
+data=[]
+for r in rows[hi+1:]:                       # one section only: a report with several kernels repeats the table
+    if r and r[0]=='Address': break
+    if len(r)==len(hdr): data.append(r)
 ia=hdr.index('Instructions Executed'); ts=hdr.index('Thread Instructions Executed'); sc=hdr.index('Source'); ss=hdr.index('# Samples')
 tot=sum(int(r[ia]) for r in data); tott=sum(int(r[ts]) for r in data); totsamp=sum(int(r[ss]) for r in data)
 print('sass instrs',len(data),'warp-instr',tot,'thread-instr',tott,'samples',totsamp)
