@@ -15,7 +15,7 @@ SO_PATH = os.environ.get("RBF_B200_LIB") or os.path.join(_HERE, "librbf_b200.so"
 
 _lib = None
 _ctx = None
-_lock = threading.Lock()
+_lock = threading.RLock()       # re-entrant: ctx() loads the library under the same lock
 
 
 class RbfError(RuntimeError):
@@ -160,6 +160,7 @@ def ctx():
     """Process-wide context on cuda:LOCAL_RANK (or RBF_DEVICE).  Raises when there is no B200."""
     global _ctx
     if _ctx is None:
+        lib()                                             # load outside the critical section too (first call may be ctx())
         with _lock:
             if _ctx is None:
                 dev = int(os.environ.get("RBF_DEVICE", os.environ.get("LOCAL_RANK", "0")))

@@ -172,3 +172,22 @@ def test_optimal_params_random_vs_reference_expression(cabi):
         assert bool(coded) == rc, (n, ones, k, l, rk, rl)
         if rc:
             assert (float(k).hex(), l) == (float(rk).hex(), rl), (n, ones)
+
+
+def test_ctx_as_first_call_does_not_deadlock():
+    """`ImprovedVideoCompressor()` as the very first use of the package calls _cabi.ctx() before _cabi.lib(): the library load
+    happens under the context lock, which therefore has to be re-entrant (a plain Lock hung scripts/gop_fps.py for good).
+    Run in a fresh interpreter with a watchdog; without a GPU the call must fail with RbfError, not hang."""
+    import subprocess
+    import sys
+    code = ("import faulthandler, sys; faulthandler.dump_traceback_later(60, exit=True)\n"
+            "sys.path.insert(0, %r)\n"
+            "from new_bloom_filter_repo_b200 import _cabi\n"
+            "try:\n"
+            "    _cabi.ctx()\n"
+            "    print('ctx ok')\n"
+            "except _cabi.RbfError as e:\n"
+            "    print('RbfError', str(e)[:60])\n") % ROOT
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr[-500:]
+    assert "ctx ok" in res.stdout or "RbfError" in res.stdout
