@@ -85,6 +85,25 @@ class FixedVideoCompressor:
                 parts.append(struct.pack("<II", *plane.shape))
         return b"".join(parts)
 
+    def compress_frame_async(self, frame, pool):
+        """compress_frame with the (up to four) zlib level-9 blobs as separate jobs of `pool`; returns a callable that assembles
+        exactly the bytes compress_frame(frame) returns.  The keyframe of a GOP is the longest serial piece of compress_video."""
+        info = getattr(frame, "yuv_info", None)
+        raws = [frame.tobytes()] + ([info[name].tobytes() for name in ("y_plane", "u_plane", "v_plane")] if info is not None else [])
+        futs = [pool.submit(zlib.compress, r, 9) for r in raws]
+
+        def assemble() -> bytes:
+            z = [f.result() for f in futs]
+            parts: List[bytes] = [struct.pack("<III", frame.shape[0], frame.shape[1], frame.dtype.itemsize),
+                                  struct.pack("<I", len(z[0])), z[0], struct.pack("<B", 1 if info is not None else 0)]
+            if info is not None:
+                fmt = info.get("format", "YUV444").encode("utf-8")
+                parts += [struct.pack("<H", len(fmt)), fmt]
+                for zi, name in zip(z[1:], ("y_plane", "u_plane", "v_plane")):
+                    parts += [struct.pack("<I", len(zi)), zi, struct.pack("<II", *info[name].shape)]
+            return b"".join(parts)
+        return assemble
+
     def decompress_frame(self, data: bytes):                                     # fvc:76-181
         h, w, isz = struct.unpack_from("<III", data, 0)
         (zlen,) = struct.unpack_from("<I", data, 12)

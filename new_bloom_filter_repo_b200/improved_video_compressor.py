@@ -446,13 +446,14 @@ class ImprovedVideoCompressor:
         keyframes = 0
         with ThreadPoolExecutor(self.num_threads) as pool:
             # keyframes (zlib level 9 of whole frames, fvc:31) start in the pool first; the GPU encodes the groups meanwhile
-            key_jobs = {i: pool.submit(self.compressor.compress_frame, frames[i]) for i in range(len(frames)) if i not in set(inter)}
+            inter_set = set(inter)
+            key_jobs = {i: self.compressor.compress_frame_async(frames[i], pool) for i in range(len(frames)) if i not in inter_set}
             payloads = self._encode_inter_frames(datas, inter, pool)
             for i, f in enumerate(frames):
                 fut = payloads.get(i)
                 if fut is None:
                     kj = key_jobs.get(i)
-                    pl = kj.result() if kj is not None else self.compressor.compress_frame(f)
+                    pl = kj() if kj is not None else self.compressor.compress_frame(f)
                     keyframes += 1
                 else:
                     pl = fut.result()

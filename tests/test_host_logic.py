@@ -48,3 +48,18 @@ def test_shard_partition():
             assert seen == list(range(pairs))
             sizes = [shard_pairs(pairs, r, world)[1] - shard_pairs(pairs, r, world)[0] for r in range(world)]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_keyframe_async_assembly_equals_serial():
+    """The GOP loop compresses a keyframe's zlib blobs as separate pool jobs: the assembled payload is byte-identical."""
+    from concurrent.futures import ThreadPoolExecutor
+    from new_bloom_filter_repo_b200.fixed_video_compressor import FixedVideoCompressor
+    c = FixedVideoCompressor(verbose=False)
+    rng = np.random.default_rng(0)
+    with ThreadPoolExecutor(3) as pool:
+        for shape, dt in (((48, 64, 3), np.uint8), ((32, 40), np.uint8), ((20, 24, 3), np.uint16)):
+            f = rng.integers(0, 200, shape).astype(dt)
+            assert c.compress_frame_async(f, pool)() == c.compress_frame(f)
+            if f.ndim == 3:
+                y = c.add_yuv_info_to_frame(f)
+                assert c.compress_frame_async(y, pool)() == c.compress_frame(y)
