@@ -1,5 +1,6 @@
 // rbf_k3_query.cuh -- K3: Bloom test of all n positions -> pass mask (ivc:245-253, ivc:116-138): per-lane, staged rings, decade tiles.  Included by rbf_kernels.cu inside namespace rbf.
 #pragma once
+#include <type_traits>
 
 // ------------------------------------------------------------------------------------------
 // K3: query.  Persistent CTAs split the batch's centuries evenly; for every frame segment the
@@ -505,11 +506,12 @@ __device__ __noinline__ void query_slab_tiled2(const FilterK K, uint32_t sm_addr
             uint32_t nproc = last_tile ? tot2 : (tot2 & ~31u);
             if (nproc == 0u && rem != 0u) nproc = tot2;              // a record is carried over one tile at most
             const uint32_t yoff = (uint32_t)(h * TY);
-#pragma unroll 1
-            for (uint32_t b = 0; b < nproc; b += 32u) {
+            // one batch of 32 records; FULL batches (all but the last of a slab) carry no per-lane validity logic
+            auto stage_b = [&](const uint32_t b, auto full) {
+                constexpr bool FULL = decltype(full)::value;
                 const uint32_t g = b + lane;
-                const bool have = g < nproc;
-                const uint32_t rec = lds32(buf_addr + 4u * min(g, (uint32_t)(Cfg::BUF - 1)));
+                const bool have = FULL ? true : (g < nproc);
+                const uint32_t rec = lds32(buf_addr + 4u * (FULL ? g : min(g, (uint32_t)(Cfg::BUF - 1))));
                 const uint32_t owner = (rec >> Cfg::IDXB) & 31u;
                 uint32_t y = (rec >> (Cfg::IDXB + 5)) + yoff, xr = x;
                 uint64_t D2o = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)D2, owner) |
@@ -547,7 +549,11 @@ __device__ __noinline__ void query_slab_tiled2(const FilterK K, uint32_t sm_addr
                 } else {
                     deliver_pass(pacc_addr, tag, ok != 0u);
                 }
-            }
+            };
+            uint32_t bb = 0;
+#pragma unroll 1
+            for (; bb + 32u <= nproc; bb += 32u) stage_b(bb, std::true_type{});
+            if (bb < nproc) stage_b(bb, std::false_type{});
             // ---- carry the leftover (< 32 records) to the front of the buffer
             const uint32_t nrem = tot2 - nproc;
             if (nrem != 0u) {
