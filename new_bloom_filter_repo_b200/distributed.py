@@ -197,7 +197,8 @@ class ShardedStreamEncoder:
     on the block and exchanges the packed bit arrays with ONE all-gather, after which every rank holds the bit array of every
     pair of the stream.  The per-pair headers (l, |w|, p, k, ones, raw) travel as a small object gather next to it."""
 
-    def __init__(self, dist, height: int, width: int, channels: int, dtype, total_frames: int, gather: str = "p2p"):
+    def __init__(self, dist, height: int, width: int, channels: int, dtype, total_frames: int, gather: str = "p2p",
+                 max_l_bits: int = None):
         from .stream import FrameStream
         self.dist = dist
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
@@ -210,6 +211,8 @@ class ShardedStreamEncoder:
         self._send = self._recv = self._peer = None
         self._nccl_ready = False
         self.results = None
+        if max_l_bits:                                        # size the all-gather slots for the densest frame expected, up front
+            self._ensure_buffers(int(max_l_bits))
 
     def upload(self, frames_of_this_rank: np.ndarray) -> None:
         if frames_of_this_rank.shape[0] != self.layout["frames"]:
@@ -242,14 +245,24 @@ class ShardedStreamEncoder:
     def encode(self, threshold: float, **kw):
         """Code this rank's block and enqueue the exchange (it overlaps the next encode; complete after `gathered()` / rbf_sync)."""
         self.results = self.stream.encode_consecutive(self.layout["frames"], threshold, **kw)
-        if self.slot == 0 or max(r.l for r in self.results) > 8 * self.slot:
-            self._ensure_buffers(max(r.l for r in self.results))
+        max_l = max(r.l for r in self.results)
+        if self.slot == 0:                                   # first encode: every rank is here, the agreement is collective
+            self._ensure_buffers(max_l)                       # no head room: pass max_l_bits to the constructor for varying densities
+        elif max_l > 8 * self.slot:
+            # growing the slot is a collective decision; one rank must not start it alone (the others would never join)
+            raise _cabi.RbfError("a bit array of %d bits does not fit the agreed all-gather slot of %d bytes: call renegotiate() on "
+                                 "every rank (e.g. with the largest l expected) and encode again" % (max_l, self.slot))
         if self._peer is not None:
             self._peer.exchange(self.stream)
         else:
             _cabi.check(_cabi.lib().rbf_stream_allgather_bitmaps(self.stream._h, self.layout["slots"], self.slot, self._send.ptr,
                                                                  self._recv.ptr), _cabi.ctx())
         return self.results
+
+    def renegotiate(self, max_l_bits: int) -> None:
+        """Collective: re-agree the slot size (max over ranks of the given bound) and re-create the exchange buffers."""
+        self.slot = 0
+        self._ensure_buffers(int(max_l_bits))
 
     def gathered(self) -> np.ndarray:
         """uint8[total_pairs, slot]: the packbits bit array of every pair of the stream, in stream order (host copy)."""
