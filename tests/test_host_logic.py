@@ -63,3 +63,42 @@ def test_keyframe_async_assembly_equals_serial():
             if f.ndim == 3:
                 y = c.add_yuv_info_to_frame(f)
                 assert c.compress_frame_async(y, pool)() == c.compress_frame(y)
+
+
+def test_bench_counters_go_stale_with_the_sources(tmp_path, monkeypatch):
+    """bench.py reports roofline.traffic / issue_frac only while the kernel sources still hash to what was profiled."""
+    import json
+    import bench
+    c = bench.kernel_counters("k_query4")
+    assert c is not None and c["stale"] is False and c["dram_bytes_per_pair"] > 1e5 and 50 < c["thread_inst_per_px"] < 200
+    fake = tmp_path / "profiles"
+    fake.mkdir()
+    c2 = dict(c, sources_sha16="0" * 16)
+    c2.pop("stale")
+    (fake / "r02_k_query4_counters.json").write_text(json.dumps(c2))
+    import os
+    for name in c["sources"]:                                  # same sources, different recorded hash -> stale
+        os.makedirs(os.path.dirname(tmp_path / name), exist_ok=True)
+        (tmp_path / name).write_bytes(open(os.path.join(bench.ROOT, name), "rb").read())
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench.kernel_counters("k_query4")["stale"] is True
+    assert bench.kernel_counters("k_no_such_kernel") is None
+
+
+def test_bench_stream_frames_equals_fill_stream_slices():
+    """Strong scaling: a rank builds only frames lo..hi of the shared stream; they must equal the full stream's slice."""
+    import bench
+    for dt in (np.uint8, np.uint16):
+        full = np.empty((9, 24, 40, 3), dt)
+        bench.fill_stream(full, seed=3)
+        for lo, hi in ((0, 3), (3, 8), (7, 8)):
+            out = np.empty((hi - lo + 1, 24, 40, 3), dt)
+            bench.stream_frames(9, 24, 40, 3, lo, hi, out)
+            assert np.array_equal(out, full[lo:hi + 1])
+
+
+def test_bench_host_cores_is_positive_and_bounded():
+    import os
+    import bench
+    n = bench.host_cores()
+    assert 1 <= n <= (os.cpu_count() or 1)
