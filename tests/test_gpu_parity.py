@@ -568,10 +568,7 @@ def test_median5_resident_frame_matches_cv2(pkg):
     st.close()
 
 
-# ------------------------------------------------------------------ exchange over peer memory (single rank here; N > 1: bench.py --gather p2p --verify-gather)
-@pytest.mark.skipif(os.environ.get("RBF_TEST_PEER") != "1",
-                    reason="single-rank twin of the peer-memory exchange (RBF_TEST_PEER=1); the multi-rank path is covered by "
-                           "test_two_ranks_p2p_equals_nccl and by bench.py's gather_verified at N = 2 / 8")
+# ------------------------------------------------------------------ exchange over peer memory (single rank here; N > 1: test_two_ranks_p2p_equals_nccl, bench.py)
 def test_peer_gather_single_rank(pkg):
     from new_bloom_filter_repo_b200 import distributed as rdist
     cabi = pkg._cabi
